@@ -1,0 +1,179 @@
+/*
+ * jxb200.h -- C ABI of libjxb200.so: the B200 (sm_100a) exact-LMM association scan.
+ *
+ * This is the drop-in boundary for JanusX's exact LMM path.  Each entry point replaces one PyO3
+ * function of the reference extension module `janusx.janusx` (registered at src/lib.rs:911-941);
+ * the reference symbol and its file:line are cited on every declaration.  INTEGRATION.md shows the
+ * binding a JanusX maintainer would add (a Rust `extern "C"` block behind the existing #[pyfunction]
+ * signatures, and the ctypes binding this repository ships in janusx_b200/_cabi.py).
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no C++/torch types.  All matrices row-major, dense unless an `ld`
+ *     argument says otherwise.
+ *   - return 0 on success, <0 on failure; jxb_last_error() returns a thread-local message.
+ *     Per-SNP numerical failure is NOT an error: the row is NaN, NaN, 1.0[, ...] like the reference
+ *     (src/stats/lmm.rs:74-91).
+ *   - `*_host` arguments are host pointers (pageable or pinned); the library stages them.  Functions
+ *     ending in `_dev` take device pointers on the model's device and do not synchronise the host
+ *     unless stated.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef JXB200_H
+#define JXB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct jxb_model jxb_model; /* opaque: the null model resident in HBM + scan workspace */
+
+/* genetic model: src/decode/decode.rs:99-146 */
+enum { JXB_MODEL_ADD = 0, JXB_MODEL_DOM = 1, JXB_MODEL_REC = 2, JXB_MODEL_HET = 3 };
+
+/* per-SNP optimiser settings: brent_minimize_with_init, src/math/brent.rs:16-136 */
+typedef struct {
+    double low, high;      /* bounds on log10(lambda) */
+    double tol;            /* reference default 1e-2 */
+    int32_t max_iter;      /* reference default 30 (CLI) / 50 (API) */
+    int32_t has_init;      /* 1 => every SNP starts at init_log10_lbd (seed_with_init_guess) */
+    double init_log10_lbd;
+    int32_t has_nullml;    /* LMM: append plrt column.  LMM2: must be 1 (or fit with jxb_ml_null). */
+    double nullml;
+} jxb_solve_cfg;
+
+/* QC thresholds of the unified BED scan: src/stats/lmm.rs:1262-1323 */
+typedef struct {
+    float maf_thr, miss_thr, het_thr;
+    int32_t genetic_model; /* JXB_MODEL_* */
+} jxb_qc_cfg;
+
+const char* jxb_last_error(void);
+int jxb_device_count(void);
+/* Returns the library build tag ("jxb200 sm_100a ..."); used by the loader to prove the native path. */
+const char* jxb_build_info(void);
+/* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
+uint64_t jxb_launch_count(void);
+
+/* ---- null model ---------------------------------------------------------------------------------
+ * Holds S[n], Xcov[n,p], y_rot[n] (f64) and, when u_t is given, U^T[n,n] (f32 values, widened to a
+ * K-padded f64 copy in HBM: 8*n*round_up(n,16) bytes).  Replaces the borrowed numpy views every
+ * reference LMM function takes (s, xcov, y_rot, u_t), e.g. src/stats/lmm.rs:1479-1495. */
+int jxb_model_create(int device, size_t n, size_t p, const double* s_host, const double* xcov_host,
+                     const double* y_rot_host, const float* u_t_host /* nullable */, jxb_model** out);
+/* Same, from device-resident buffers (e.g. after an NCCL broadcast done by the caller). u_t_dev is
+ * f32[n,n] row-major, nullable.  The buffers are copied; the caller keeps ownership. */
+int jxb_model_create_dev(int device, size_t n, size_t p, const double* s_dev, const double* xcov_dev,
+                         const double* y_rot_dev, const float* u_t_dev, jxb_model** out);
+void jxb_model_destroy(jxb_model* m);
+/* Replace Xcov / y_rot (same n, p) without re-uploading U^T: a new trait on the same GRM. */
+int jxb_model_set_xy(jxb_model* m, const double* xcov_host, const double* y_rot_host);
+int jxb_model_sync(jxb_model* m);
+
+/* lmm_rotate_x_y_with_ut_f64 -- src/stats/reml.rs:107-198.  x_host f64[n,q], y_host f64[n] ->
+ * x_rot_host f64[n,q], y_rot_host f64[n].  Needs a model created with U^T (S/Xcov/y may be dummies). */
+int jxb_rotate_xy(jxb_model* m, const double* x_host, size_t q, const double* y_host, double* x_rot_host,
+                  double* y_rot_host);
+
+/* lmm_reml_null_f32 -- src/stats/reml.rs:570-616.  out3 = (lambda, ml, reml). */
+int jxb_reml_null(jxb_model* m, double low, double high, int max_iter, double tol, double out3[3]);
+/* ml_loglike_null_f32 -- src/stats/reml.rs:618-646. */
+int jxb_ml_loglike_null(jxb_model* m, double log10_lbd, double* ml);
+/* null ML by Brent inside lmm_reml_lmm2_assoc_bed_to_tsv_f32 -- src/stats/lmm.rs:2901-2924.
+ * out2 = (log10 lambda_ml, ml0). */
+int jxb_ml_null(jxb_model* m, double low, double high, int max_iter, double tol, int has_init, double init,
+                double out2[2]);
+
+/* lmm_reml_chunk_f32 -- src/stats/lmm.rs:333-518.  g_rot_host f32[m,n] already rotated.
+ * out_host f64[m, has_nullml ? 4 : 3] = beta, se, pwald[, plrt].  evals_host (nullable) i32[m]. */
+int jxb_lmm_reml_chunk_f32(jxb_model* m, const float* g_rot_host, size_t rows, const jxb_solve_cfg* cfg,
+                           double* out_host, int32_t* evals_host);
+/* lmm_reml_chunk_from_snp_f32 -- src/stats/lmm.rs:1479-1630.  snp_host f32[m,n] centred genotypes. */
+int jxb_lmm_reml_chunk_from_snp_f32(jxb_model* m, const float* snp_host, size_t rows, const jxb_solve_cfg* cfg,
+                                    double* out_host, int32_t* evals_host);
+/* lmm_reml_lmm2_chunk_from_snp_f32 -- src/stats/lmm.rs:1632-1780.  out_host f64[m,6] =
+ * beta, se, pwald, lambda_reml, ml_alt, plrt.  `rotated` != 0 => snp_host is already rotated. */
+int jxb_lmm2_chunk_f32(jxb_model* m, const float* snp_host, size_t rows, int rotated, const jxb_solve_cfg* cfg,
+                       double* out_host, int32_t* evals_host);
+/* lmm_assoc_chunk_f32 / lmm_assoc_chunk_from_snp_f32 / fvlmm_assoc_* (fixed lambda) --
+ * src/stats/lmm.rs:2010-2238, src/stats/fvlmm.rs:1484-1563, 1691-1805.
+ * out_host f64[m, nullml ? 4 : 3].  meta3 (nullable) = (ypy, log_det_v, df). */
+int jxb_lmm_fixed_chunk_f32(jxb_model* m, const float* snp_host, size_t rows, int rotated, double log10_lbd,
+                            const double* nullml /* nullable */, double* out_host, double meta3[3]);
+
+/* Rotation only (rotate_snp_block_with_ut_blas, src/stats/lmm.rs:728-783): snp_host f32[m,n] ->
+ * rot_host f32[m,n].  variant 0 = DMMA/TMA kernel, 1 = CUDA-core cross-check kernel. */
+int jxb_rotate_block_f32(jxb_model* m, const float* snp_host, size_t rows, float* rot_host, int variant);
+
+/* Packed scan: the producer+consumer body of run_unified_bed_scan_to_tsv_common
+ * (src/stats/lmm.rs:1140-1432) for one batch of packed SNP rows:
+ * count -> QC -> decode/impute/centre -> rotate -> per-SNP solve.
+ *   packed_host u8[rows, bytes_per_snp] (PLINK SNP-major payload, 4 samples per byte)
+ *   sample_idx_host nullable i64[n] (positions of the model's samples in FAM order); NULL = identity
+ *   pre_keep_host nullable u8[rows]: extra host-side row mask (e.g. snps_only allele filter)
+ *   mode 0 = LMM (3|4 cols), 1 = LMM2 (6 cols), 2 = fixed lambda at cfg->init_log10_lbd (3|4 cols)
+ * Outputs (all host, indexed by SOURCE row unless stated):
+ *   keep_host u8[rows], af_host f32[rows], missing_host i32[rows]
+ *   out_host f64[n_kept, out_cols] compacted in SNP order; *n_kept_host = rows kept
+ *   evals_host nullable i32[n_kept] */
+int jxb_scan_packed(jxb_model* m, const uint8_t* packed_host, size_t bytes_per_snp, size_t rows, size_t n_full,
+                    const int64_t* sample_idx_host, const uint8_t* pre_keep_host, const jxb_qc_cfg* qc,
+                    const jxb_solve_cfg* cfg, int mode, uint8_t* keep_host, float* af_host, int32_t* missing_host,
+                    double* out_host, int32_t* evals_host, size_t* n_kept_host);
+/* Same with the packed batch already in HBM (bench.py `value`; multi-GPU shards).  Results stay on the
+ * device in the model workspace; fetch with jxb_scan_fetch.  Asynchronous on the model's stream. */
+int jxb_scan_packed_dev(jxb_model* m, const uint8_t* packed_dev, size_t bytes_per_snp, size_t rows, size_t n_full,
+                        const int64_t* sample_idx_dev, const jxb_qc_cfg* qc, const jxb_solve_cfg* cfg, int mode);
+int jxb_scan_fetch(jxb_model* m, size_t rows, int out_cols, uint8_t* keep_host, float* af_host,
+                   int32_t* missing_host, double* out_host, int32_t* evals_host, size_t* n_kept_host);
+
+/* K1 alone, for parity tests: counts + QC + decode/centre of one packed batch.
+ *   g_host nullable f32[n_kept, n] (compacted), counts_host i32[rows,4] = missing, het, hom_alt, keep */
+int jxb_decode_packed(jxb_model* m, const uint8_t* packed_host, size_t bytes_per_snp, size_t rows, size_t n_full,
+                      const int64_t* sample_idx_host, const jxb_qc_cfg* qc, int32_t* counts_host, float* af_host,
+                      float* miss_rate_host, float* g_host, size_t* n_kept_host);
+
+/* Per-stage device timers of the last jxb_scan_packed* call, milliseconds:
+ * [0]=count+qc+compact [1]=decode [2]=rotate [3]=solve [4]=h2d [5]=d2h.  (The reference's
+ * JX_LMM_UNIFIED_STAGE_TIMING, src/stats/lmm.rs:2711-2742.)  Enabled by jxb_set_timing(1). */
+void jxb_set_timing(int on);
+int jxb_last_stage_ms(jxb_model* m, float ms6[6]);
+/* raw stream handle (cudaStream_t) the model launches on, for callers timing with CUDA events */
+void* jxb_model_stream(jxb_model* m);
+/* choose the rotation kernel for subsequent scans: 0 = DMMA/TMA (default), 1 = CUDA-core cross-check */
+void jxb_set_rotate_variant(int variant);
+
+/* ---- file level ------------------------------------------------------------------------------------
+ * lmm_reml_assoc_bed_to_tsv_f32 / lmm_reml_lmm2_assoc_bed_to_tsv_f32 / fvlmm_assoc_bed_to_tsv_f32 --
+ * src/stats/lmm.rs:2488-2750, 2753-3038; src/stats/fvlmm.rs:2482-2527.  Streams prefix.bed/.bim/.fam,
+ * writes the reference TSV schema (src/io/assoc2tsv.rs:45-57, 430-517), SNP order preserved.
+ * Warm start across SNPs (schedule-dependent in the reference, src/stats/lmm.rs:134-161) is never
+ * used: rows equal the reference run with JX_LMM_UNIFIED_NO_WARM_START=1. */
+typedef int (*jxb_progress_cb)(size_t done, size_t total, void* user); /* nonzero return aborts */
+typedef struct {
+    const char* bed_prefix;
+    const char* out_tsv;
+    jxb_qc_cfg qc;
+    jxb_solve_cfg solve;
+    int32_t mode;              /* 0 LMM, 1 LMM2, 2 fixed lambda (solve.init_log10_lbd) */
+    int32_t snps_only;
+    const char* const* sample_ids; /* nullable; n entries (IIDs) */
+    size_t n_sample_ids;
+    size_t batch_rows;         /* SNP rows per device batch (reference: rotate_block_rows) */
+    size_t snp_begin, snp_end; /* scan [begin,end) of BED rows; end==0 => all (multi-GPU shards) */
+    int32_t write_header;
+    size_t progress_every;
+} jxb_bed_scan_cfg;
+int jxb_scan_bed_to_tsv(jxb_model* m, const jxb_bed_scan_cfg* cfg, size_t* rows_written, jxb_progress_cb cb,
+                        void* user);
+
+/* TSV row formatter (append_assoc_row_from_fields, src/io/assoc2tsv.rs:430-517); exported for tests.
+ * Returns bytes written. */
+size_t jxb_format_row(char* buf, size_t cap, const char* chrom, int64_t pos, const char* snp, const char* a0,
+                      const char* a1, float af, float miss_rate, const double* row, int out_cols);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

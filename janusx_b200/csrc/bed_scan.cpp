@@ -1,0 +1,425 @@
+// bed_scan.cpp -- host side of the BED -> TSV scan: PLINK readers, batch loop, TSV formatting.
+//
+// Replaces, for the B200 path:
+//   run_unified_bed_scan_to_tsv_common (producer/consumer loop)   src/stats/lmm.rs:975-1477
+//   read_fam / BimChunkReader / parse_bim_line                     src/io/gfcore.rs:112-324, 1426-1478
+//   append_assoc_row_from_fields + header schemas                  src/io/assoc2tsv.rs:45-57, 430-517
+//   AsyncTsvWriter (writer thread)                                 src/stats/common.rs:374-468
+//   resolve_snp_name                                               src/stats/lmm.rs:1952-1958
+//
+// The device work of each batch is jxb_scan_packed (K1 -> K2 -> K3).  A writer thread formats and
+// writes batch i while the GPU runs batch i+1 (the reference's double buffer, src/io/pipeline.rs:49-92).
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <cerrno>
+#include <cmath>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <fstream>
+#include <mutex>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/jxb200.h"
+
+namespace jxb {
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+}  // namespace jxb
+
+namespace {
+
+// Rust `{:.N}`: C "%.Nf" with Rust's spellings of the non-finite values
+size_t fmt_fixed(char* buf, size_t cap, double v, int prec) {
+    if (std::isnan(v)) return (size_t)snprintf(buf, cap, "NaN");
+    if (std::isinf(v)) return (size_t)snprintf(buf, cap, v > 0 ? "inf" : "-inf");
+    return (size_t)snprintf(buf, cap, "%.*f", prec, v);
+}
+
+// Rust `{:.Ne}`: mantissa as C "%.Ne", exponent without sign padding or leading zeros
+size_t fmt_exp(char* buf, size_t cap, double v, int prec) {
+    if (std::isnan(v)) return (size_t)snprintf(buf, cap, "NaN");
+    if (std::isinf(v)) return (size_t)snprintf(buf, cap, v > 0 ? "inf" : "-inf");
+    char tmp[64];
+    int len = snprintf(tmp, sizeof tmp, "%.*e", prec, v);
+    int epos = len - 1;
+    while (epos > 0 && tmp[epos] != 'e') --epos;
+    const int ex = atoi(tmp + epos + 1);
+    tmp[epos] = '\0';
+    return (size_t)snprintf(buf, cap, "%se%d", tmp, ex);
+}
+
+struct Site {
+    std::string chrom, snp, a0, a1;
+    int64_t pos = 0;
+};
+
+std::vector<std::string> split_ws(const std::string& line) {
+    std::vector<std::string> out;
+    size_t i = 0, n = line.size();
+    while (i < n) {
+        while (i < n && isspace((unsigned char)line[i])) ++i;
+        size_t j = i;
+        while (j < n && !isspace((unsigned char)line[j])) ++j;
+        if (j > i) out.emplace_back(line.substr(i, j - i));
+        i = j;
+    }
+    return out;
+}
+
+// Rust str::parse::<i32>(): optional sign, decimal digits only, range-checked; failure -> 0
+int64_t parse_i32_or_zero(const std::string& s) {
+    if (s.empty()) return 0;
+    size_t i = 0;
+    bool neg = false;
+    if (s[0] == '+' || s[0] == '-') { neg = s[0] == '-'; i = 1; }
+    if (i >= s.size()) return 0;
+    int64_t v = 0;
+    for (; i < s.size(); ++i) {
+        if (s[i] < '0' || s[i] > '9') return 0;
+        v = v * 10 + (s[i] - '0');
+        if (v > 2147483648LL) return 0;
+    }
+    v = neg ? -v : v;
+    if (v < -2147483648LL || v > 2147483647LL) return 0;
+    return v;
+}
+
+bool simple_snp_allele(const std::string& a) {
+    size_t b = 0, e = a.size();
+    while (b < e && isspace((unsigned char)a[b])) ++b;
+    while (e > b && isspace((unsigned char)a[e - 1])) --e;
+    if (e - b != 1) return false;
+    const char c = (char)toupper((unsigned char)a[b]);
+    return c == 'A' || c == 'C' || c == 'G' || c == 'T';
+}
+
+struct BimReader {
+    std::ifstream in;
+    std::string path;
+    size_t next_row = 0;
+    bool open(const std::string& prefix) {
+        path = prefix + ".bim";
+        in.open(path);
+        return in.good();
+    }
+    // returns 0 ok, 1 EOF, -1 malformed
+    int next(Site& s, std::string& err) {
+        std::string line;
+        if (!std::getline(in, line)) return 1;
+        ++next_row;
+        auto tok = split_ws(line);
+        if (tok.size() < 6) {
+            while (!line.empty() && isspace((unsigned char)line.back())) line.pop_back();
+            err = "Malformed BIM line at " + path + ":" + std::to_string(next_row) + ": " + line;
+            return -1;
+        }
+        s.chrom = tok[0];
+        s.snp = tok[1];
+        s.pos = parse_i32_or_zero(tok[3]);
+        s.a0 = tok[4];
+        s.a1 = tok[5];
+        return 0;
+    }
+};
+
+struct Batch {
+    std::vector<Site> sites;      // per source row
+    std::vector<uint8_t> keep;
+    std::vector<float> af;
+    std::vector<int32_t> missing;
+    std::vector<double> out;      // compacted
+    size_t n_kept = 0;
+    int out_cols = 3;
+};
+
+struct Writer {
+    FILE* fp = nullptr;
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<Batch*> q;
+    bool done = false;
+    bool io_error = false;
+    size_t n_model = 0;
+    size_t rows_written = 0;
+
+    void run() {
+        std::string text;
+        char buf[2048];
+        for (;;) {
+            Batch* b = nullptr;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return done || !q.empty(); });
+                if (q.empty()) return;
+                b = q.front();
+                q.pop_front();
+            }
+            cv.notify_all();
+            text.clear();
+            size_t k = 0;
+            for (size_t r = 0; r < b->keep.size(); ++r) {
+                if (!b->keep[r]) continue;
+                const Site& s = b->sites[r];
+                // lmm.rs:2667-2670: miss column = missing_count as f32 / n as f32
+                const float mr = n_model ? (float)b->missing[r] / (float)n_model : 0.0f;
+                const size_t len = jxb_format_row(buf, sizeof buf, s.chrom.c_str(), s.pos, s.snp.c_str(),
+                                                  s.a0.c_str(), s.a1.c_str(), b->af[r], mr,
+                                                  b->out.data() + k * b->out_cols, b->out_cols);
+                text.append(buf, len);
+                ++k;
+            }
+            if (!text.empty() && fwrite(text.data(), 1, text.size(), fp) != text.size()) io_error = true;
+            rows_written += k;
+            delete b;
+        }
+    }
+    void push(Batch* b) {
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return q.size() < 4; });
+            q.push_back(b);
+        }
+        cv.notify_all();
+    }
+    void finish() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            done = true;
+        }
+        cv.notify_all();
+        if (th.joinable()) th.join();
+    }
+};
+
+const char* header_for(int out_cols) {
+    switch (out_cols) {
+        case 4: return "chrom\tpos\tsnp\tallele0\tallele1\taf\tmiss\tbeta\tse\tchisq\tpwald\tplrt\n";
+        case 6: return "chrom\tpos\tsnp\tallele0\tallele1\taf\tmiss\tbeta\tse\tchisq\tpwald\tlambda\tml\tplrt\n";
+        default: return "chrom\tpos\tsnp\tallele0\tallele1\taf\tmiss\tbeta\tse\tchisq\tpwald\n";
+    }
+}
+
+}  // namespace
+
+extern "C" size_t jxb_format_row(char* buf, size_t cap, const char* chrom, int64_t pos, const char* snp,
+                                 const char* a0, const char* a1, float af, float miss_rate, const double* row,
+                                 int out_cols) {
+    const double beta = row[0], se = row[1];
+    const bool valid = std::isfinite(beta) && std::isfinite(se) && se > 0.0;
+    // sanitize_assoc_pvalue, src/math/linalg.rs:99-108
+    double pw = 1.0;
+    if (valid) {
+        const double p = row[2];
+        if (std::isfinite(p)) pw = p < 2.2250738585072014e-308 ? 2.2250738585072014e-308 : (p > 1.0 ? 1.0 : p);
+    }
+    // chisq_from_beta_se_and_optional_plrt, src/math/linalg.rs:288-298
+    double chisq = NAN;
+    if (valid) { const double z = beta / se; chisq = z * z; }
+    char* w = buf;
+    char* end = buf + cap;
+    auto put_s = [&](const char* s) { w += snprintf(w, (size_t)(end - w), "%s", s); };
+    auto tab = [&]() { if (w < end - 1) *w++ = '\t'; };
+    put_s(chrom); tab();
+    w += snprintf(w, (size_t)(end - w), "%lld", (long long)pos); tab();
+    if (snp[0] == '\0' || (snp[0] == '.' && snp[1] == '\0')) {
+        w += snprintf(w, (size_t)(end - w), "%s_%lld", chrom, (long long)pos);
+    } else {
+        put_s(snp);
+    }
+    tab();
+    put_s(a0); tab();
+    put_s(a1); tab();
+    w += fmt_fixed(w, (size_t)(end - w), (double)af, 4); tab();
+    w += fmt_fixed(w, (size_t)(end - w), (double)miss_rate, 4); tab();
+    w += fmt_fixed(w, (size_t)(end - w), beta, 4); tab();
+    w += fmt_fixed(w, (size_t)(end - w), se, 4); tab();
+    w += fmt_exp(w, (size_t)(end - w), chisq, 4); tab();
+    w += fmt_exp(w, (size_t)(end - w), pw, 4);
+    if (out_cols == 4) {
+        tab(); w += fmt_exp(w, (size_t)(end - w), row[3], 4);
+    } else if (out_cols == 6) {
+        tab(); w += fmt_exp(w, (size_t)(end - w), row[3], 6);
+        tab(); w += fmt_exp(w, (size_t)(end - w), row[4], 6);
+        tab(); w += fmt_exp(w, (size_t)(end - w), row[5], 4);
+    }
+    if (w < end - 1) *w++ = '\n';
+    *w = '\0';
+    return (size_t)(w - buf);
+}
+
+extern "C" int jxb_scan_bed_to_tsv(jxb_model* m, const jxb_bed_scan_cfg* cfg, size_t* rows_written,
+                                   jxb_progress_cb cb, void* user) {
+    using jxb::fail;
+    if (!m || !cfg || !cfg->bed_prefix || !cfg->out_tsv) return fail(-2, "null argument");
+    const std::string prefix = cfg->bed_prefix;
+
+    // FAM (gfcore.rs:307-324)
+    std::vector<std::string> fam;
+    {
+        std::ifstream f(prefix + ".fam");
+        if (!f.good()) return fail(-20, "open " + prefix + ".fam: No such file or directory");
+        std::string line;
+        while (std::getline(f, line)) {
+            auto tok = split_ws(line);
+            if (tok.size() < 2) return fail(-21, "Malformed FAM line: " + line);
+            fam.push_back(tok[1]);
+        }
+    }
+    const size_t n_full = fam.size();
+    if (n_full == 0) return fail(-22, "no samples in PLINK FAM");
+
+    // sample mapping (lmm.rs:1010-1039)
+    std::vector<int64_t> sidx;
+    bool identity = true;
+    size_t n = n_full;
+    if (cfg->sample_ids) {
+        std::unordered_map<std::string, size_t> pos;
+        for (size_t i = 0; i < fam.size(); ++i) pos[fam[i]] = i;  // later duplicates win, like HashMap::collect
+        sidx.resize(cfg->n_sample_ids);
+        for (size_t k = 0; k < cfg->n_sample_ids; ++k) {
+            auto it = pos.find(cfg->sample_ids[k]);
+            if (it == pos.end()) return fail(-23, std::string("sample '") + cfg->sample_ids[k] + "' not found in PLINK FAM");
+            sidx[k] = (int64_t)it->second;
+        }
+        n = sidx.size();
+        identity = (n == n_full);
+        for (size_t k = 0; identity && k < n; ++k) identity = (sidx[k] == (int64_t)k);
+    }
+
+    // BED (lmm.rs:1041-1076)
+    const size_t bps = (n_full + 3) / 4;
+    const std::string bed_path = prefix + ".bed";
+    int fd = open(bed_path.c_str(), O_RDONLY);
+    if (fd < 0) return fail(-24, "open " + bed_path + ": " + strerror(errno));
+    struct stat st;
+    fstat(fd, &st);
+    const size_t fsize = (size_t)st.st_size;
+    const uint8_t* map = fsize ? (const uint8_t*)mmap(nullptr, fsize, PROT_READ, MAP_PRIVATE, fd, 0) : nullptr;
+    close(fd);
+    if (fsize && map == MAP_FAILED) return fail(-25, "mmap " + bed_path + ": " + strerror(errno));
+    auto unmap = [&]() { if (map && fsize) munmap((void*)map, fsize); };
+    if (fsize < 3 || map[0] != 0x6C || map[1] != 0x1B || map[2] != 0x01) {
+        unmap();
+        return fail(-26, "only SNP-major BED supported");
+    }
+    const size_t data_len = fsize - 3;
+    if (data_len % bps != 0) {
+        unmap();
+        return fail(-27, "BED payload length " + std::to_string(data_len) + " not a multiple of " + std::to_string(bps));
+    }
+    const size_t n_snps = data_len / bps;
+    const size_t begin = cfg->snp_begin < n_snps ? cfg->snp_begin : n_snps;
+    const size_t end = (cfg->snp_end == 0 || cfg->snp_end > n_snps) ? n_snps : cfg->snp_end;
+    const uint8_t* payload = map + 3;
+
+    BimReader bim;
+    if (!bim.open(prefix)) { unmap(); return fail(-28, "open " + prefix + ".bim: No such file or directory"); }
+    std::string err;
+    Site skip;
+    while (bim.next_row < begin) {
+        int r = bim.next(skip, err);
+        if (r != 0) {
+            unmap();
+            return fail(-29, r < 0 ? err : "BIM ended early: needed row " + std::to_string(begin) + " but only saw " +
+                                               std::to_string(bim.next_row) + " rows from " + bim.path);
+        }
+    }
+
+    jxb_solve_cfg solve = cfg->solve;
+    const int mode = cfg->mode;
+    // lmm.rs:2573-2575: a finite seed is clamped into [low, high]
+    if (solve.has_init && mode != 2) {
+        if (!std::isfinite(solve.init_log10_lbd)) solve.has_init = 0;
+        else solve.init_log10_lbd = std::min(std::max(solve.init_log10_lbd, solve.low), solve.high);
+    }
+    if (mode == 1 && !solve.has_nullml) {
+        // lmm.rs:2901-2924: fit the null ML with the same Brent settings
+        double o2[2];
+        int rc = jxb_ml_null(m, solve.low, solve.high, solve.max_iter, solve.tol, solve.has_init, solve.init_log10_lbd, o2);
+        if (rc) { unmap(); return rc; }
+        if (!std::isfinite(o2[1])) { unmap(); return fail(-30, "failed to optimize null ML for LMM2 unified scan"); }
+        solve.has_nullml = 1;
+        solve.nullml = o2[1];
+    }
+    const int out_cols = mode == 1 ? 6 : (solve.has_nullml ? 4 : 3);
+
+    Writer wr;
+    wr.fp = fopen(cfg->out_tsv, "wb");
+    if (!wr.fp) { unmap(); return fail(-31, std::string("create ") + cfg->out_tsv + ": " + strerror(errno)); }
+    static thread_local std::vector<char> iobuf;
+    iobuf.resize(8u << 20);
+    setvbuf(wr.fp, iobuf.data(), _IOFBF, iobuf.size());
+    if (cfg->write_header) fputs(header_for(out_cols), wr.fp);
+    wr.n_model = n;
+    wr.th = std::thread([&wr] { wr.run(); });
+
+    const size_t total = end - begin;
+    const size_t step = std::max<size_t>(1, std::min<size_t>(cfg->batch_rows ? cfg->batch_rows : 4096, std::max<size_t>(total, 1)));
+    size_t next_emit = cfg->progress_every ? std::max<size_t>(1, std::min(cfg->progress_every, total)) : 0;
+    int rc = 0;
+    std::vector<uint8_t> pre_keep;
+    for (size_t c0 = begin; c0 < end && rc == 0; c0 += step) {
+        const size_t rows = std::min(step, end - c0);
+        Batch* b = new Batch();
+        b->sites.resize(rows);
+        b->keep.resize(rows);
+        b->af.resize(rows);
+        b->missing.resize(rows);
+        b->out.resize(rows * out_cols);
+        b->out_cols = out_cols;
+        for (size_t r = 0; r < rows; ++r) {
+            int br = bim.next(b->sites[r], err);
+            if (br != 0) {
+                rc = fail(-29, br < 0 ? err : "BIM ended early: needed row " + std::to_string(c0 + rows) +
+                                                  " but only saw " + std::to_string(bim.next_row) + " rows from " + bim.path);
+                break;
+            }
+        }
+        if (rc) { delete b; break; }
+        const uint8_t* mask = nullptr;
+        if (cfg->snps_only) {
+            pre_keep.assign(rows, 1);
+            for (size_t r = 0; r < rows; ++r)
+                if (!simple_snp_allele(b->sites[r].a0) || !simple_snp_allele(b->sites[r].a1)) pre_keep[r] = 0;
+            mask = pre_keep.data();
+        }
+        rc = jxb_scan_packed(m, payload + c0 * bps, bps, rows, n_full, identity ? nullptr : sidx.data(), mask, &cfg->qc,
+                             &solve, mode, b->keep.data(), b->af.data(), b->missing.data(), b->out.data(), nullptr,
+                             &b->n_kept);
+        if (rc) { delete b; break; }
+        wr.push(b);
+        const size_t scanned = c0 + rows - begin;
+        if (cb && next_emit && scanned >= next_emit) {
+            if (cb(scanned < total ? scanned : total, total, user) != 0) { rc = fail(-40, "interrupted by progress callback"); break; }
+            next_emit = std::min((scanned / cfg->progress_every + 1) * cfg->progress_every, total);
+        }
+    }
+    if (rc == 0 && end == n_snps) {
+        // gfcore.rs:265-280: the BIM must not hold more rows than the BED
+        Site extra;
+        int br = bim.next(extra, err);
+        if (br != 1)
+            rc = fail(-32, "BIM site count exceeds BED SNP count: expected " + std::to_string(n_snps) +
+                               ", saw extra row " + std::to_string(bim.next_row) + " in " + bim.path);
+    }
+    if (rc == 0 && cb) cb(total, total, user);
+    wr.finish();
+    const bool ioerr = wr.io_error || fclose(wr.fp) != 0;
+    unmap();
+    if (rc) return rc;
+    if (ioerr) return fail(-33, std::string("write ") + cfg->out_tsv + " failed");
+    if (rows_written) *rows_written = wr.rows_written;
+    return 0;
+}

@@ -1,0 +1,664 @@
+// cabi.cu -- C ABI of libjxb200.so (see include/jxb200.h): model residency, staging, batch pipeline.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/jxb200.h"
+#include "jxb_common.cuh"
+
+struct jxb_model {
+    jxb::Model m;
+    bool timing_ready = false;
+    cudaEvent_t ev[8];
+    float stage_ms[6] = {0, 0, 0, 0, 0, 0};
+    float* missr = nullptr;       // [cap_rows] device
+    uint8_t* mask = nullptr;      // [cap_rows] device (pre-keep mask)
+    double* scal = nullptr;       // small device scratch (null fit outputs)
+    size_t last_rows = 0;
+    int last_out_cols = 0;
+};
+
+namespace jxb {
+
+static thread_local std::string g_err;
+static std::atomic<uint64_t> g_launches{0};
+static int g_timing = 0;
+static int g_rotate_variant = 0;
+
+void set_error(const std::string& msg) { g_err = msg; }
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+void note_launch(int k) { g_launches.fetch_add((uint64_t)k, std::memory_order_relaxed); }
+
+namespace {
+
+__global__ void widen_ut_kernel(const float* __restrict__ src, size_t n, size_t row0, size_t rows,
+                                double* __restrict__ dst, size_t ldk) {
+    for (size_t r = blockIdx.y; r < rows; r += gridDim.y) {
+        const float* s = src + r * n;
+        double* d = dst + (row0 + r) * ldk;
+        for (size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x; j < n; j += (size_t)gridDim.x * blockDim.x)
+            d[j] = (double)s[j];
+    }
+}
+
+__global__ void apply_mask_kernel(int32_t* counts, const uint8_t* mask, int rows) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < rows && mask[r] == 0) counts[4 * r + 3] = 0;
+}
+
+template <class T>
+int dev_alloc(T** p, size_t count) {
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    if (count == 0) return 0;
+    JXB_CUDA_OK(cudaMalloc((void**)p, count * sizeof(T)));
+    return 0;
+}
+
+int upload_small(Model& m, const double* s, const double* xcov, const double* y) {
+    const size_t n = m.n, p = m.p;
+    std::vector<double> xt(p * m.ldn, 0.0);
+    for (size_t i = 0; i < n; ++i)
+        for (size_t r = 0; r < p; ++r) xt[r * m.ldn + i] = xcov[i * p + r];
+    if (s) JXB_CUDA_OK(cudaMemcpyAsync(m.s, s, n * sizeof(double), cudaMemcpyHostToDevice, m.stream));
+    JXB_CUDA_OK(cudaMemcpyAsync(m.y, y, n * sizeof(double), cudaMemcpyHostToDevice, m.stream));
+    JXB_CUDA_OK(cudaMemcpyAsync(m.xt, xt.data(), xt.size() * sizeof(double), cudaMemcpyHostToDevice, m.stream));
+    JXB_CUDA_OK(cudaStreamSynchronize(m.stream));
+    m.fx_valid = false;
+    return 0;
+}
+
+int widen_ut(Model& m, const float* u_t, bool on_device) {
+    const size_t n = m.n;
+    JXB_CUDA_OK(cudaMemsetAsync(m.ut, 0, m.n_pad * m.ldk * sizeof(double), m.stream));
+    // stage in row slabs of <= 256 MiB so the temporary never doubles the footprint
+    const size_t slab_rows = std::max<size_t>(1, std::min<size_t>(n, (256u << 20) / (n * sizeof(float) + 1)));
+    float* tmp = nullptr;
+    if (!on_device) JXB_CUDA_OK(cudaMalloc((void**)&tmp, slab_rows * n * sizeof(float)));
+    for (size_t r0 = 0; r0 < n; r0 += slab_rows) {
+        const size_t rows = std::min(slab_rows, n - r0);
+        const float* src = u_t + r0 * n;
+        if (!on_device) {
+            JXB_CUDA_OK(cudaMemcpyAsync(tmp, src, rows * n * sizeof(float), cudaMemcpyHostToDevice, m.stream));
+            src = tmp;
+        }
+        dim3 grid((unsigned)std::min<size_t>((n + 255) / 256, 64), (unsigned)std::min<size_t>(rows, 2048));
+        widen_ut_kernel<<<grid, 256, 0, m.stream>>>(src, n, r0, rows, m.ut, m.ldk);
+        note_launch(1);
+        JXB_CUDA_OK(cudaGetLastError());
+        if (!on_device) JXB_CUDA_OK(cudaStreamSynchronize(m.stream));
+    }
+    JXB_CUDA_OK(cudaStreamSynchronize(m.stream));
+    if (tmp) cudaFree(tmp);
+    return 0;
+}
+
+int model_alloc(int device, size_t n, size_t p, bool with_ut, jxb_model** out) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+        return fail(-1, "no CUDA device is visible: libjxb200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(-2, "device index out of range");
+    if (n == 0) return fail(-2, "y must not be empty");
+    if (p < 1 || p > 32) return fail(-2, "Xcov must have between 1 and 32 columns");
+    if (n > (size_t)0x7fffffff) return fail(-2, "n too large");
+    JXB_CUDA_OK(cudaSetDevice(device));
+    jxb_model* h = new jxb_model();
+    Model& m = h->m;
+    m.device = device;
+    m.n = n;
+    m.p = p;
+    m.ldn = round_up(n, 32);
+    m.ldk = round_up(n, kRotBK);
+    m.n_pad = round_up(n, kRotBN);
+    m.ldc = round_up(n, 32);
+    JXB_CUDA_OK(cudaStreamCreateWithFlags(&m.stream, cudaStreamNonBlocking));
+    int rc = 0;
+    rc |= dev_alloc(&m.s, n);
+    rc |= dev_alloc(&m.y, n);
+    rc |= dev_alloc(&m.xt, p * m.ldn);
+    rc |= dev_alloc(&m.n_kept, 8);
+    rc |= dev_alloc(&h->scal, 16);
+    rc |= dev_alloc(&m.fx_w, m.ldn);
+    rc |= dev_alloc(&m.fx_py, m.ldn);
+    rc |= dev_alloc(&m.fx_wx, p * m.ldn);
+    rc |= dev_alloc(&m.fx_scal, 8 + 32 * 32);
+    if (with_ut) rc |= dev_alloc(&m.ut, m.n_pad * m.ldk);
+    if (rc) { jxb_model_destroy(h); return rc; }
+    *out = h;
+    return 0;
+}
+
+int ensure_capacity(jxb_model* h, size_t rows, size_t bps, bool need_g) {
+    Model& m = h->m;
+    JXB_CUDA_OK(cudaSetDevice(m.device));
+    if (rows > m.cap_rows) {
+        JXB_CUDA_OK(cudaStreamSynchronize(m.stream));
+        const size_t cap = round_up(std::max<size_t>(rows, 256), kRotBM);
+        int rc = 0;
+        rc |= dev_alloc(&m.rot, cap * m.ldc);
+        rc |= dev_alloc(&m.out, cap * 8);
+        rc |= dev_alloc(&m.evals, cap);
+        rc |= dev_alloc(&m.counts, cap * 4);
+        rc |= dev_alloc(&m.af, cap);
+        rc |= dev_alloc(&h->missr, cap);
+        rc |= dev_alloc(&h->mask, cap);
+        rc |= dev_alloc(&m.src_row, cap);
+        if (m.g64) { cudaFree(m.g64); m.g64 = nullptr; }
+        if (m.packed) { cudaFree(m.packed); m.packed = nullptr; m.bps_cap = 0; }
+        if (rc) return rc;
+        m.cap_rows = cap;
+    }
+    if (need_g && !m.g64) {
+        JXB_CUDA_OK(cudaMalloc((void**)&m.g64, m.cap_rows * m.ldk * sizeof(double)));
+        JXB_CUDA_OK(cudaMemsetAsync(m.g64, 0, m.cap_rows * m.ldk * sizeof(double), m.stream));
+        if (m.ut) {
+            int rc = make_tensor_maps(m);
+            if (rc) return rc;
+        }
+    }
+    if (bps > 0 && (bps > m.bps_cap || !m.packed)) {
+        JXB_CUDA_OK(cudaStreamSynchronize(m.stream));
+        if (m.packed) cudaFree(m.packed);
+        m.packed = nullptr;
+        JXB_CUDA_OK(cudaMalloc((void**)&m.packed, m.cap_rows * bps));
+        m.bps_cap = bps;
+    }
+    return 0;
+}
+
+int ensure_stage_f32(Model& m, size_t count) {
+    if (count > m.stage_f32_cap) {
+        JXB_CUDA_OK(cudaStreamSynchronize(m.stream));
+        if (m.stage_f32) cudaFree(m.stage_f32);
+        m.stage_f32 = nullptr;
+        JXB_CUDA_OK(cudaMalloc((void**)&m.stage_f32, count * sizeof(float)));
+        m.stage_f32_cap = count;
+    }
+    return 0;
+}
+
+int ensure_sample_idx(Model& m, const int64_t* idx, size_t n_sel, bool on_device) {
+    if (n_sel > m.n_sel_cap) {
+        JXB_CUDA_OK(cudaStreamSynchronize(m.stream));
+        if (m.sample_idx) cudaFree(m.sample_idx);
+        m.sample_idx = nullptr;
+        JXB_CUDA_OK(cudaMalloc((void**)&m.sample_idx, n_sel * sizeof(int64_t)));
+        m.n_sel_cap = n_sel;
+    }
+    JXB_CUDA_OK(cudaMemcpyAsync(m.sample_idx, idx, n_sel * sizeof(int64_t),
+                                on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, m.stream));
+    return 0;
+}
+
+void tick(jxb_model* h, int i) {
+    if (!g_timing) return;
+    if (!h->timing_ready) {
+        for (auto& e : h->ev) cudaEventCreate(&e);
+        h->timing_ready = true;
+    }
+    cudaEventRecord(h->ev[i], h->m.stream);
+}
+
+SolveParams to_params(const jxb_solve_cfg* c, int mode) {
+    SolveParams sp;
+    sp.low = c->low; sp.high = c->high; sp.tol = c->tol; sp.max_iter = c->max_iter;
+    sp.has_init = c->has_init; sp.init = c->init_log10_lbd;
+    sp.has_nullml = c->has_nullml; sp.nullml = c->nullml;
+    sp.mode = mode;
+    return sp;
+}
+
+int check_cfg(const jxb_solve_cfg* c, int mode) {
+    if (!c) return fail(-2, "solve cfg is null");
+    if (mode != 2) {
+        if (!(c->low < c->high)) return fail(-2, "low must be < high");
+        if (!(std::isfinite(c->tol) && c->tol > 0.0)) return fail(-2, "tol must be positive and finite");
+        if (c->max_iter < 0) return fail(-2, "max_iter must be >= 0");
+    }
+    if (mode == 1 && !c->has_nullml) return fail(-2, "LMM2 needs nullml (fit it with jxb_ml_null)");
+    if (mode == 1 && !std::isfinite(c->nullml)) return fail(-2, "nullml must be finite when provided");
+    return 0;
+}
+
+int out_cols_of(const jxb_solve_cfg* c, int mode) { return mode == 1 ? 6 : (c->has_nullml ? 4 : 3); }
+
+// rotated f32 block already in m.rot -> out
+int run_solve(jxb_model* h, size_t rows, const int32_t* n_rows_dev, const jxb_solve_cfg* cfg, int mode) {
+    Model& m = h->m;
+    const int oc = out_cols_of(cfg, mode);
+    h->last_out_cols = oc;
+    if (mode == 2) {
+        if (!m.fx_valid || m.fx_log10_lbd != cfg->init_log10_lbd) {
+            int rc = launch_fixed_prepare(m, cfg->init_log10_lbd, m.stream);
+            note_launch(1);
+            if (rc) return rc;
+            double st[4];
+            JXB_CUDA_OK(cudaMemcpyAsync(st, m.fx_scal, sizeof st, cudaMemcpyDeviceToHost, m.stream));
+            JXB_CUDA_OK(cudaStreamSynchronize(m.stream));
+            if (st[3] == -1.0) return fail(-10, "non-positive s[i]+lbd");
+            if (st[3] == -2.0) return fail(-11, "X'WX not SPD");
+            if (st[3] == -3.0) return fail(-12, "df <= 0");
+            m.fx_valid = true;
+            m.fx_log10_lbd = cfg->init_log10_lbd;
+        }
+        note_launch(1);
+        return launch_fixed_solve(m, m.rot, m.ldc, rows, n_rows_dev, cfg->has_nullml, cfg->nullml, m.out, oc, m.stream);
+    }
+    note_launch(1);
+    return launch_solve(m, m.rot, m.ldc, rows, n_rows_dev, to_params(cfg, mode), m.out, oc, m.evals, m.n_kept + 1,
+                        m.stream);
+}
+
+// f32 host block -> (optionally rotate) -> solve -> host
+int chunk_common(jxb_model* h, const float* host, size_t rows, bool rotated, const jxb_solve_cfg* cfg, int mode,
+                 double* out_host, int32_t* evals_host) {
+    if (!h) return fail(-2, "model is null");
+    int rc = check_cfg(cfg, mode);
+    if (rc) return rc;
+    Model& m = h->m;
+    if (rows == 0) return 0;
+    if (!rotated && !m.ut) return fail(-3, "u_t must be (n, n) and row-major U^T");
+    rc = ensure_capacity(h, rows, 0, !rotated);
+    if (rc) return rc;
+    const size_t n = m.n;
+    if (rotated) {
+        JXB_CUDA_OK(cudaMemcpy2DAsync(m.rot, m.ldc * sizeof(float), host, n * sizeof(float), n * sizeof(float), rows,
+                                      cudaMemcpyHostToDevice, m.stream));
+    } else {
+        rc = ensure_stage_f32(m, rows * n);
+        if (rc) return rc;
+        JXB_CUDA_OK(cudaMemcpyAsync(m.stage_f32, host, rows * n * sizeof(float), cudaMemcpyHostToDevice, m.stream));
+        rc = launch_widen_f32(m.stage_f32, n, rows, n, m.g64, m.ldk, m.stream);
+        note_launch(1);
+        if (rc) return rc;
+        rc = launch_rotate(m, rows, nullptr, m.stream, g_rotate_variant);
+        note_launch(1);
+        if (rc) return rc;
+    }
+    rc = run_solve(h, rows, nullptr, cfg, mode);
+    if (rc) return rc;
+    const int oc = h->last_out_cols;
+    JXB_CUDA_OK(cudaMemcpyAsync(out_host, m.out, rows * oc * sizeof(double), cudaMemcpyDeviceToHost, m.stream));
+    if (evals_host && mode != 2)
+        JXB_CUDA_OK(cudaMemcpyAsync(evals_host, m.evals, rows * sizeof(int32_t), cudaMemcpyDeviceToHost, m.stream));
+    JXB_CUDA_OK(cudaStreamSynchronize(m.stream));
+    return 0;
+}
+
+int scan_device_stages(jxb_model* h, const uint8_t* packed_dev, size_t bps, size_t rows, size_t n_full,
+                       const int64_t* sidx_dev, size_t n_sel, bool have_mask, const jxb_qc_cfg* qc,
+                       const jxb_solve_cfg* cfg, int mode) {
+    Model& m = h->m;
+    int rc;
+    tick(h, 1);
+    rc = launch_count_qc(m, packed_dev, bps, rows, n_full, sidx_dev, n_sel, qc->maf_thr, qc->miss_thr, qc->het_thr,
+                         m.counts, m.af, h->missr, m.stream);
+    note_launch(1);
+    if (rc) return rc;
+    if (have_mask) {
+        apply_mask_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, m.stream>>>(m.counts, h->mask, (int)rows);
+        note_launch(1);
+    }
+    rc = launch_compact(m.counts, rows, m.src_row, m.n_kept, m.stream);
+    note_launch(1);
+    if (rc) return rc;
+    tick(h, 2);
+    rc = launch_decode_center(packed_dev, bps, m.src_row, m.n_kept, rows, n_full, sidx_dev, m.n, m.af, m.counts,
+                              qc->genetic_model, m.g64, m.ldk, nullptr, 0, m.stream);
+    note_launch(1);
+    if (rc) return rc;
+    tick(h, 3);
+    rc = launch_rotate(m, rows, m.n_kept, m.stream, g_rotate_variant);
+    note_launch(1);
+    if (rc) return rc;
+    tick(h, 4);
+    rc = run_solve(h, rows, m.n_kept, cfg, mode);
+    if (rc) return rc;
+    tick(h, 5);
+    h->last_rows = rows;
+    return 0;
+}
+
+int check_scan_args(jxb_model* h, size_t bps, size_t n_full, const int64_t* sidx, const jxb_qc_cfg* qc) {
+    if (!h) return fail(-2, "model is null");
+    if (!qc) return fail(-2, "qc cfg is null");
+    if (!h->m.ut) return fail(-3, "u_t must be (n, n) row-major U^T");
+    if (n_full == 0) return fail(-2, "no samples in PLINK FAM");
+    if (bps != (n_full + 3) / 4) return fail(-2, "bytes_per_snp must equal ceil(n_full/4)");
+    if (!sidx && n_full != h->m.n) return fail(-2, "sample_ids length != expected sample count");
+    if (qc->genetic_model < 0 || qc->genetic_model > 3) return fail(-2, "model must be one of: add, dom, rec, het");
+    return 0;
+}
+
+}  // namespace
+}  // namespace jxb
+
+using namespace jxb;
+
+extern "C" {
+
+const char* jxb_last_error(void) { return g_err.c_str(); }
+
+int jxb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+const char* jxb_build_info(void) { return "jxb200 sm_100a cuda-kernels: k1_decode k2_rotate(dmma884+tma) k3_solve"; }
+
+uint64_t jxb_launch_count(void) { return g_launches.load(); }
+
+void jxb_set_timing(int on) { g_timing = on; }
+void jxb_set_rotate_variant(int variant) { g_rotate_variant = variant; }
+
+int jxb_model_create(int device, size_t n, size_t p, const double* s, const double* xcov, const double* y,
+                     const float* u_t, jxb_model** out) {
+    if (!out || !s || !xcov || !y) return fail(-2, "null argument");
+    jxb_model* h = nullptr;
+    int rc = model_alloc(device, n, p, u_t != nullptr, &h);
+    if (rc) return rc;
+    rc = upload_small(h->m, s, xcov, y);
+    if (!rc && u_t) rc = widen_ut(h->m, u_t, false);
+    if (rc) { jxb_model_destroy(h); return rc; }
+    *out = h;
+    return 0;
+}
+
+int jxb_model_create_dev(int device, size_t n, size_t p, const double* s_dev, const double* xcov_dev,
+                         const double* y_dev, const float* u_t_dev, jxb_model** out) {
+    if (!out || !s_dev || !xcov_dev || !y_dev) return fail(-2, "null argument");
+    jxb_model* h = nullptr;
+    int rc = model_alloc(device, n, p, u_t_dev != nullptr, &h);
+    if (rc) return rc;
+    std::vector<double> s(n), x(n * p), y(n);
+    cudaError_t e = cudaMemcpy(s.data(), s_dev, n * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(x.data(), xcov_dev, n * p * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(y.data(), y_dev, n * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { jxb_model_destroy(h); return fail(-100, cudaGetErrorString(e)); }
+    rc = upload_small(h->m, s.data(), x.data(), y.data());
+    if (!rc && u_t_dev) rc = widen_ut(h->m, u_t_dev, true);
+    if (rc) { jxb_model_destroy(h); return rc; }
+    *out = h;
+    return 0;
+}
+
+void jxb_model_destroy(jxb_model* h) {
+    if (!h) return;
+    Model& m = h->m;
+    cudaSetDevice(m.device);
+    if (m.stream) cudaStreamSynchronize(m.stream);
+    void* ptrs[] = {m.s, m.y, m.xt, m.ut, m.g64, m.rot, m.out, m.evals, m.packed, m.counts, m.af, m.src_row,
+                    m.n_kept, m.sample_idx, m.stage_f32, m.fx_w, m.fx_py, m.fx_wx, m.fx_scal, h->missr, h->mask,
+                    h->scal};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (h->timing_ready)
+        for (auto& e : h->ev) cudaEventDestroy(e);
+    if (m.stream) cudaStreamDestroy(m.stream);
+    if (m.tmap_ut) free(m.tmap_ut);
+    if (m.tmap_g) free(m.tmap_g);
+    delete h;
+}
+
+int jxb_model_set_xy(jxb_model* h, const double* xcov, const double* y) {
+    if (!h || !xcov || !y) return fail(-2, "null argument");
+    JXB_CUDA_OK(cudaSetDevice(h->m.device));
+    return upload_small(h->m, nullptr, xcov, y);
+}
+
+int jxb_model_sync(jxb_model* h) {
+    if (!h) return fail(-2, "model is null");
+    JXB_CUDA_OK(cudaSetDevice(h->m.device));
+    JXB_CUDA_OK(cudaStreamSynchronize(h->m.stream));
+    return 0;
+}
+
+void* jxb_model_stream(jxb_model* h) { return h ? (void*)h->m.stream : nullptr; }
+
+int jxb_rotate_xy(jxb_model* h, const double* x, size_t q, const double* y, double* x_rot, double* y_rot) {
+    if (!h || !x || !y || !x_rot || !y_rot) return fail(-2, "null argument");
+    Model& m = h->m;
+    if (!m.ut) return fail(-3, "u_t must be shape (n, n) and row-major U^T");
+    JXB_CUDA_OK(cudaSetDevice(m.device));
+    const size_t n = m.n;
+    double *dx = nullptr, *dy = nullptr, *dxr = nullptr, *dyr = nullptr;
+    JXB_CUDA_OK(cudaMalloc((void**)&dx, std::max<size_t>(1, n * q) * sizeof(double)));
+    JXB_CUDA_OK(cudaMalloc((void**)&dy, n * sizeof(double)));
+    JXB_CUDA_OK(cudaMalloc((void**)&dxr, std::max<size_t>(1, n * q) * sizeof(double)));
+    JXB_CUDA_OK(cudaMalloc((void**)&dyr, n * sizeof(double)));
+    int rc = 0;
+    cudaMemcpyAsync(dx, x, n * q * sizeof(double), cudaMemcpyHostToDevice, m.stream);
+    cudaMemcpyAsync(dy, y, n * sizeof(double), cudaMemcpyHostToDevice, m.stream);
+    rc = launch_rotate_xy(m, nullptr, dx, q, dy, dxr, dyr, m.stream);
+    note_launch(1);
+    if (!rc) {
+        cudaMemcpyAsync(x_rot, dxr, n * q * sizeof(double), cudaMemcpyDeviceToHost, m.stream);
+        cudaMemcpyAsync(y_rot, dyr, n * sizeof(double), cudaMemcpyDeviceToHost, m.stream);
+        cudaError_t e = cudaStreamSynchronize(m.stream);
+        if (e != cudaSuccess) rc = fail(-100, cudaGetErrorString(e));
+    }
+    cudaFree(dx); cudaFree(dy); cudaFree(dxr); cudaFree(dyr);
+    return rc;
+}
+
+static int null_common(jxb_model* h, int kind, double low, double high, int max_iter, double tol, int has_init,
+                       double init, double* out, int n_out) {
+    if (!h || !out) return fail(-2, "null argument");
+    Model& m = h->m;
+    JXB_CUDA_OK(cudaSetDevice(m.device));
+    int rc = launch_null_fit(m, kind, low, high, max_iter, tol, has_init, init, h->scal, m.stream);
+    note_launch(1);
+    if (rc) return rc;
+    JXB_CUDA_OK(cudaMemcpyAsync(out, h->scal, n_out * sizeof(double), cudaMemcpyDeviceToHost, m.stream));
+    JXB_CUDA_OK(cudaStreamSynchronize(m.stream));
+    return 0;
+}
+
+int jxb_reml_null(jxb_model* h, double low, double high, int max_iter, double tol, double out3[3]) {
+    if (!(low < high)) return fail(-2, "low must be < high");
+    return null_common(h, 0, low, high, max_iter, tol, 0, 0.0, out3, 3);
+}
+
+int jxb_ml_loglike_null(jxb_model* h, double log10_lbd, double* ml) {
+    return null_common(h, 2, 0, 0, 0, 0, 1, log10_lbd, ml, 1);
+}
+
+int jxb_ml_null(jxb_model* h, double low, double high, int max_iter, double tol, int has_init, double init,
+                double out2[2]) {
+    if (!(low < high)) return fail(-2, "low must be < high");
+    return null_common(h, 1, low, high, max_iter, tol, has_init, init, out2, 2);
+}
+
+int jxb_lmm_reml_chunk_f32(jxb_model* h, const float* g_rot, size_t rows, const jxb_solve_cfg* cfg, double* out,
+                           int32_t* evals) {
+    return chunk_common(h, g_rot, rows, true, cfg, 0, out, evals);
+}
+
+int jxb_lmm_reml_chunk_from_snp_f32(jxb_model* h, const float* snp, size_t rows, const jxb_solve_cfg* cfg,
+                                    double* out, int32_t* evals) {
+    return chunk_common(h, snp, rows, false, cfg, 0, out, evals);
+}
+
+int jxb_lmm2_chunk_f32(jxb_model* h, const float* snp, size_t rows, int rotated, const jxb_solve_cfg* cfg,
+                       double* out, int32_t* evals) {
+    return chunk_common(h, snp, rows, rotated != 0, cfg, 1, out, evals);
+}
+
+int jxb_lmm_fixed_chunk_f32(jxb_model* h, const float* snp, size_t rows, int rotated, double log10_lbd,
+                            const double* nullml, double* out, double meta3[3]) {
+    if (!h) return fail(-2, "model is null");
+    if (h->m.n <= h->m.p + 1) return fail(-2, "n must be > p_cov+1");
+    jxb_solve_cfg cfg;
+    std::memset(&cfg, 0, sizeof cfg);
+    cfg.has_init = 1;
+    cfg.init_log10_lbd = log10_lbd;
+    cfg.has_nullml = nullml ? 1 : 0;
+    cfg.nullml = nullml ? *nullml : 0.0;
+    int rc = chunk_common(h, snp, rows, rotated != 0, &cfg, 2, out, nullptr);
+    if (rc) return rc;
+    if (meta3 && rows > 0) {
+        JXB_CUDA_OK(cudaMemcpy(meta3, h->m.fx_scal, 3 * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+
+int jxb_rotate_block_f32(jxb_model* h, const float* snp, size_t rows, float* rot_host, int variant) {
+    if (!h || !snp || !rot_host) return fail(-2, "null argument");
+    Model& m = h->m;
+    if (!m.ut) return fail(-3, "u_t must be (n, n) and row-major U^T");
+    if (rows == 0) return 0;
+    int rc = ensure_capacity(h, rows, 0, true);
+    if (rc) return rc;
+    const size_t n = m.n;
+    rc = ensure_stage_f32(m, rows * n);
+    if (rc) return rc;
+    JXB_CUDA_OK(cudaMemcpyAsync(m.stage_f32, snp, rows * n * sizeof(float), cudaMemcpyHostToDevice, m.stream));
+    rc = launch_widen_f32(m.stage_f32, n, rows, n, m.g64, m.ldk, m.stream);
+    note_launch(1);
+    if (rc) return rc;
+    rc = launch_rotate(m, rows, nullptr, m.stream, variant);
+    note_launch(1);
+    if (rc) return rc;
+    JXB_CUDA_OK(cudaMemcpy2DAsync(rot_host, n * sizeof(float), m.rot, m.ldc * sizeof(float), n * sizeof(float), rows,
+                                  cudaMemcpyDeviceToHost, m.stream));
+    JXB_CUDA_OK(cudaStreamSynchronize(m.stream));
+    return 0;
+}
+
+int jxb_scan_packed_dev(jxb_model* h, const uint8_t* packed_dev, size_t bps, size_t rows, size_t n_full,
+                        const int64_t* sidx_dev, const jxb_qc_cfg* qc, const jxb_solve_cfg* cfg, int mode) {
+    int rc = check_scan_args(h, bps, n_full, sidx_dev, qc);
+    if (rc) return rc;
+    rc = check_cfg(cfg, mode);
+    if (rc) return rc;
+    if (rows == 0) { h->last_rows = 0; return 0; }
+    rc = ensure_capacity(h, rows, 0, true);
+    if (rc) return rc;
+    return scan_device_stages(h, packed_dev, bps, rows, n_full, sidx_dev, h->m.n, false, qc, cfg, mode);
+}
+
+int jxb_scan_fetch(jxb_model* h, size_t rows, int out_cols, uint8_t* keep_host, float* af_host, int32_t* missing_host,
+                   double* out_host, int32_t* evals_host, size_t* n_kept_host) {
+    if (!h) return fail(-2, "model is null");
+    Model& m = h->m;
+    JXB_CUDA_OK(cudaSetDevice(m.device));
+    if (rows == 0) { if (n_kept_host) *n_kept_host = 0; return 0; }
+    if (rows > m.cap_rows) return fail(-2, "rows exceeds the last scan");
+    std::vector<int32_t> counts(rows * 4);
+    int32_t nk = 0;
+    JXB_CUDA_OK(cudaMemcpyAsync(counts.data(), m.counts, rows * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, m.stream));
+    JXB_CUDA_OK(cudaMemcpyAsync(&nk, m.n_kept, sizeof(int32_t), cudaMemcpyDeviceToHost, m.stream));
+    if (af_host) JXB_CUDA_OK(cudaMemcpyAsync(af_host, m.af, rows * sizeof(float), cudaMemcpyDeviceToHost, m.stream));
+    JXB_CUDA_OK(cudaStreamSynchronize(m.stream));
+    if (out_host && nk > 0)
+        JXB_CUDA_OK(cudaMemcpyAsync(out_host, m.out, (size_t)nk * out_cols * sizeof(double), cudaMemcpyDeviceToHost, m.stream));
+    if (evals_host && nk > 0)
+        JXB_CUDA_OK(cudaMemcpyAsync(evals_host, m.evals, (size_t)nk * sizeof(int32_t), cudaMemcpyDeviceToHost, m.stream));
+    tick(h, 6);
+    JXB_CUDA_OK(cudaStreamSynchronize(m.stream));
+    for (size_t r = 0; r < rows; ++r) {
+        if (keep_host) keep_host[r] = (uint8_t)(counts[4 * r + 3] != 0);
+        if (missing_host) missing_host[r] = counts[4 * r + 0];
+    }
+    if (n_kept_host) *n_kept_host = (size_t)nk;
+    if (g_timing && h->timing_ready) {
+        for (int i = 0; i < 6; ++i) h->stage_ms[i] = 0.f;
+        float t;
+        if (cudaEventElapsedTime(&t, h->ev[1], h->ev[2]) == cudaSuccess) h->stage_ms[0] = t;
+        if (cudaEventElapsedTime(&t, h->ev[2], h->ev[3]) == cudaSuccess) h->stage_ms[1] = t;
+        if (cudaEventElapsedTime(&t, h->ev[3], h->ev[4]) == cudaSuccess) h->stage_ms[2] = t;
+        if (cudaEventElapsedTime(&t, h->ev[4], h->ev[5]) == cudaSuccess) h->stage_ms[3] = t;
+        if (cudaEventElapsedTime(&t, h->ev[0], h->ev[1]) == cudaSuccess) h->stage_ms[4] = t;
+        if (cudaEventElapsedTime(&t, h->ev[5], h->ev[6]) == cudaSuccess) h->stage_ms[5] = t;
+    }
+    return 0;
+}
+
+int jxb_scan_packed(jxb_model* h, const uint8_t* packed, size_t bps, size_t rows, size_t n_full,
+                    const int64_t* sidx, const uint8_t* pre_keep, const jxb_qc_cfg* qc, const jxb_solve_cfg* cfg,
+                    int mode, uint8_t* keep_host, float* af_host, int32_t* missing_host, double* out_host,
+                    int32_t* evals_host, size_t* n_kept_host) {
+    int rc = check_scan_args(h, bps, n_full, sidx, qc);
+    if (rc) return rc;
+    rc = check_cfg(cfg, mode);
+    if (rc) return rc;
+    if (rows == 0) { if (n_kept_host) *n_kept_host = 0; return 0; }
+    if (!packed) return fail(-2, "packed is null");
+    Model& m = h->m;
+    rc = ensure_capacity(h, rows, bps, true);
+    if (rc) return rc;
+    tick(h, 0);
+    JXB_CUDA_OK(cudaMemcpyAsync(m.packed, packed, rows * bps, cudaMemcpyHostToDevice, m.stream));
+    const int64_t* sidx_dev = nullptr;
+    if (sidx) {
+        rc = ensure_sample_idx(m, sidx, m.n, false);
+        if (rc) return rc;
+        sidx_dev = m.sample_idx;
+    }
+    if (pre_keep) JXB_CUDA_OK(cudaMemcpyAsync(h->mask, pre_keep, rows, cudaMemcpyHostToDevice, m.stream));
+    rc = scan_device_stages(h, m.packed, bps, rows, n_full, sidx_dev, m.n, pre_keep != nullptr, qc, cfg, mode);
+    if (rc) return rc;
+    return jxb_scan_fetch(h, rows, h->last_out_cols, keep_host, af_host, missing_host, out_host, evals_host,
+                          n_kept_host);
+}
+
+int jxb_decode_packed(jxb_model* h, const uint8_t* packed, size_t bps, size_t rows, size_t n_full,
+                      const int64_t* sidx, const jxb_qc_cfg* qc, int32_t* counts_host, float* af_host,
+                      float* miss_rate_host, float* g_host, size_t* n_kept_host) {
+    if (!h || !qc || !packed) return fail(-2, "null argument");
+    if (bps != (n_full + 3) / 4) return fail(-2, "bytes_per_snp must equal ceil(n_full/4)");
+    if (!sidx && n_full != h->m.n) return fail(-2, "sample_ids length != expected sample count");
+    if (rows == 0) { if (n_kept_host) *n_kept_host = 0; return 0; }
+    Model& m = h->m;
+    int rc = ensure_capacity(h, rows, bps, false);
+    if (rc) return rc;
+    const size_t n = m.n;
+    JXB_CUDA_OK(cudaMemcpyAsync(m.packed, packed, rows * bps, cudaMemcpyHostToDevice, m.stream));
+    const int64_t* sidx_dev = nullptr;
+    if (sidx) {
+        rc = ensure_sample_idx(m, sidx, n, false);
+        if (rc) return rc;
+        sidx_dev = m.sample_idx;
+    }
+    rc = launch_count_qc(m, m.packed, bps, rows, n_full, sidx_dev, n, qc->maf_thr, qc->miss_thr, qc->het_thr, m.counts,
+                         m.af, h->missr, m.stream);
+    note_launch(1);
+    if (rc) return rc;
+    rc = launch_compact(m.counts, rows, m.src_row, m.n_kept, m.stream);
+    note_launch(1);
+    if (rc) return rc;
+    int32_t nk = 0;
+    JXB_CUDA_OK(cudaMemcpyAsync(&nk, m.n_kept, sizeof nk, cudaMemcpyDeviceToHost, m.stream));
+    if (counts_host)
+        JXB_CUDA_OK(cudaMemcpyAsync(counts_host, m.counts, rows * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, m.stream));
+    if (af_host) JXB_CUDA_OK(cudaMemcpyAsync(af_host, m.af, rows * sizeof(float), cudaMemcpyDeviceToHost, m.stream));
+    if (miss_rate_host)
+        JXB_CUDA_OK(cudaMemcpyAsync(miss_rate_host, h->missr, rows * sizeof(float), cudaMemcpyDeviceToHost, m.stream));
+    JXB_CUDA_OK(cudaStreamSynchronize(m.stream));
+    if (n_kept_host) *n_kept_host = (size_t)nk;
+    if (g_host && nk > 0) {
+        rc = ensure_stage_f32(m, (size_t)nk * n);
+        if (rc) return rc;
+        rc = launch_decode_center(m.packed, bps, m.src_row, m.n_kept, rows, n_full, sidx_dev, n, m.af, m.counts,
+                                  qc->genetic_model, nullptr, 0, m.stage_f32, n, m.stream);
+        note_launch(1);
+        if (rc) return rc;
+        JXB_CUDA_OK(cudaMemcpyAsync(g_host, m.stage_f32, (size_t)nk * n * sizeof(float), cudaMemcpyDeviceToHost, m.stream));
+        JXB_CUDA_OK(cudaStreamSynchronize(m.stream));
+    }
+    return 0;
+}
+
+int jxb_last_stage_ms(jxb_model* h, float ms6[6]) {
+    if (!h) return fail(-2, "model is null");
+    for (int i = 0; i < 6; ++i) ms6[i] = h->stage_ms[i];
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,103 @@
+// jxb_common.cuh -- shared declarations for the B200 (sm_100a) exact-LMM scan kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include <string>
+
+namespace jxb {
+
+// thread-local last error message surfaced through jxb_last_error()
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+void note_launch(int k);  // counts kernel launches for jxb_launch_count()
+
+#define JXB_CUDA_OK(expr)                                                                     \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            return ::jxb::fail(-100, std::string(#expr) + ": " + cudaGetErrorString(_e));     \
+        }                                                                                     \
+    } while (0)
+
+constexpr int kMaxCov = 16;        // covariate columns (incl. intercept) with a register-resident kernel
+constexpr int kRotBM = 128;        // rotation CTA tile (SNP rows)
+constexpr int kRotBN = 128;        // rotation CTA tile (eigen-directions)
+constexpr int kRotBK = 16;         // doubles per k-slab = one 128-byte swizzle row
+constexpr int kRotStages = 6;
+
+inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Null model resident in HBM (one per device).  Layouts (DESIGN.md "Data layout"):
+//   s[n], y[n]            f64
+//   xt[p][ldn]            f64, covariate-major (SoA) so a warp reads 32 consecutive samples
+//   ut[n_pad][ldk]        f64, row k = k-th eigenvector (U^T row-major), zero padded:
+//                         ldk = round_up(n,16) (TMA row pitch), n_pad = round_up(n,128)
+struct Model {
+    int device = 0;
+    size_t n = 0, p = 0;
+    size_t ldn = 0, ldk = 0, n_pad = 0;
+    double* s = nullptr;
+    double* y = nullptr;
+    double* xt = nullptr;
+    double* ut = nullptr;      // may be null for rotated-input-only use
+    bool owns = true;
+    // scan workspace (grown on demand)
+    size_t cap_rows = 0;
+    double* g64 = nullptr;     // [cap_rows_pad][ldk] decoded+centred genotypes (GEMM A operand)
+    float* rot = nullptr;      // [cap_rows][ldc]   rotated genotypes, f32 (reference storage type)
+    size_t ldc = 0;
+    double* out = nullptr;     // [cap_rows][8]
+    int32_t* evals = nullptr;  // [cap_rows]
+    uint8_t* packed = nullptr; // [cap_rows][bps_cap]
+    size_t bps_cap = 0;
+    int32_t* counts = nullptr; // [cap_rows][4] missing, het, hom_alt, keep
+    float* af = nullptr;       // [cap_rows]
+    int32_t* src_row = nullptr;// [cap_rows] compacted -> source row
+    int32_t* n_kept = nullptr; // device scalar (+ work counters): [0]=rows kept, [1]=solve queue, [2]=tile queue
+    int64_t* sample_idx = nullptr; size_t n_sel_cap = 0;
+    float* stage_f32 = nullptr; size_t stage_f32_cap = 0; // H2D staging for f32 inputs
+    void* tmap_ut = nullptr;   // CUtensorMap for ut (host copy, 128 B)
+    void* tmap_g = nullptr;    // CUtensorMap for g64
+    cudaStream_t stream = nullptr;
+    // fixed-lambda cache (A14)
+    float* fx_w = nullptr; float* fx_py = nullptr; float* fx_wx = nullptr; double* fx_scal = nullptr;
+    double fx_log10_lbd = 0.0; bool fx_valid = false;
+};
+
+struct SolveParams {
+    double low, high, tol;
+    int max_iter;
+    int has_init; double init;        // REML start (seed_with_init_guess)
+    int has_nullml; double nullml;    // LMM: adds plrt column.  LMM2: required.
+    int mode;                         // 0 = LMM (3|4 cols), 1 = LMM2 (6 cols)
+};
+
+// ---- kernels' host launchers (each file documents the reference lines it replaces) ----
+int launch_count_qc(const Model& m, const uint8_t* packed, size_t bps, size_t rows, size_t n_full,
+                    const int64_t* sample_idx, size_t n_sel, float maf_thr, float miss_thr, float het_thr,
+                    int32_t* counts, float* af, float* miss_rate, cudaStream_t st);
+int launch_compact(const int32_t* counts, size_t rows, int32_t* src_row, int32_t* n_kept, cudaStream_t st);
+int launch_decode_center(const uint8_t* packed, size_t bps, const int32_t* src_row, const int32_t* n_kept,
+                         size_t max_rows, size_t n_full, const int64_t* sample_idx, size_t n,
+                         const float* af_by_src, const int32_t* counts_by_src, int model_code,
+                         double* g64, size_t ldk, float* g32, size_t ld32, cudaStream_t st);
+int launch_widen_f32(const float* src, size_t ld_src, size_t rows, size_t n, double* dst, size_t ldk,
+                     cudaStream_t st);
+int launch_rotate(Model& m, size_t max_rows, const int32_t* n_rows_dev, cudaStream_t st, int variant);
+int launch_rotate_xy(const Model& m, const float* ut_f32, const double* x, size_t q, const double* y,
+                     double* x_rot, double* y_rot, cudaStream_t st);
+int launch_solve(const Model& m, const float* g_rot, size_t ldc, size_t max_rows, const int32_t* n_rows_dev,
+                 const SolveParams& sp, double* out, int out_cols, int32_t* evals, int32_t* queue,
+                 cudaStream_t st);
+int launch_null_fit(const Model& m, int kind /*0 reml-null(3 out), 1 ml-null brent(2 out), 2 ml at x(1 out)*/,
+                    double low, double high, int max_iter, double tol, int has_init, double init,
+                    double* out_dev, cudaStream_t st);
+int launch_fixed_prepare(Model& m, double log10_lbd, cudaStream_t st);
+int launch_fixed_solve(const Model& m, const float* g_rot, size_t ldc, size_t max_rows,
+                       const int32_t* n_rows_dev, int has_nullml, double nullml, double* out, int out_cols,
+                       cudaStream_t st);
+int make_tensor_maps(Model& m);
+
+}  // namespace jxb

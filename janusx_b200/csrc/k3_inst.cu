@@ -1,0 +1,28 @@
+// k3_inst.cu -- one static-covariate-count instantiation of the K3 kernels per translation unit
+// (compiled with -DJXB_P=1..8 by janusx_b200/build.py so the heavy unrolled kernels build in parallel).
+#include "k3_solve.cuh"
+
+#ifndef JXB_P
+#error "compile with -DJXB_P=<covariate columns>"
+#endif
+
+#define JXB_CAT2(a, b) a##b
+#define JXB_CAT(a, b) JXB_CAT2(a, b)
+
+namespace jxb {
+
+int JXB_CAT(k3_launch_solve_p, JXB_P)(const k3::ModelView& mv, int blocks, const float* g_rot, size_t ldc,
+                                      int max_rows, const int32_t* n_rows_dev, const SolveParams& sp, double* out,
+                                      int out_cols, int32_t* evals, int32_t* queue, cudaStream_t st) {
+    k3::solve_kernel<JXB_P, false><<<blocks, 256, 0, st>>>(mv, g_rot, ldc, max_rows, n_rows_dev, sp, out, out_cols,
+                                                            evals, queue);
+    return 0;
+}
+
+int JXB_CAT(k3_launch_null_p, JXB_P)(const k3::ModelView& mv, int kind, double low, double high, int max_iter,
+                                     double tol, int has_init, double init, double* out_dev, cudaStream_t st) {
+    k3::null_kernel<JXB_P, false><<<1, 32, 0, st>>>(mv, kind, low, high, max_iter, tol, has_init, init, out_dev);
+    return 0;
+}
+
+}  // namespace jxb

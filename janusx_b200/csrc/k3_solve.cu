@@ -1,0 +1,104 @@
+// k3_solve.cu -- host launchers for the K3 kernels (device code: k3_solve.cuh; static covariate-count
+// instantiations: k3_inst.cu compiled once per P; this unit holds the runtime-p and fixed-lambda kernels).
+#include "k3_solve.cuh"
+
+namespace jxb {
+
+#define JXB_DECL_P(P)                                                                                          \
+    int k3_launch_solve_p##P(const k3::ModelView&, int, const float*, size_t, int, const int32_t*,             \
+                             const SolveParams&, double*, int, int32_t*, int32_t*, cudaStream_t);              \
+    int k3_launch_null_p##P(const k3::ModelView&, int, double, double, int, double, int, double, double*,      \
+                            cudaStream_t);
+JXB_DECL_P(1) JXB_DECL_P(2) JXB_DECL_P(3) JXB_DECL_P(4) JXB_DECL_P(5) JXB_DECL_P(6) JXB_DECL_P(7) JXB_DECL_P(8)
+#undef JXB_DECL_P
+
+namespace {
+
+using namespace k3;
+
+ModelView view_of(const Model& m) {
+    ModelView v;
+    v.s = m.s; v.y = m.y; v.xt = m.xt; v.ldn = m.ldn; v.n = (int)m.n; v.p = (int)m.p;
+    return v;
+}
+
+int sm_count(int device) {
+    int v = 148;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device);
+    return v;
+}
+
+}  // namespace
+
+#define JXB_DISPATCH_P(P_, CALL_STATIC, CALL_DYN) \
+    switch (P_) {                                 \
+        case 1: { CALL_STATIC(1); break; }        \
+        case 2: { CALL_STATIC(2); break; }        \
+        case 3: { CALL_STATIC(3); break; }        \
+        case 4: { CALL_STATIC(4); break; }        \
+        case 5: { CALL_STATIC(5); break; }        \
+        case 6: { CALL_STATIC(6); break; }        \
+        case 7: { CALL_STATIC(7); break; }        \
+        case 8: { CALL_STATIC(8); break; }        \
+        default: { CALL_DYN(); break; }           \
+    }
+
+int launch_solve(const Model& m, const float* g_rot, size_t ldc, size_t max_rows, const int32_t* n_rows_dev,
+                 const SolveParams& sp, double* out, int out_cols, int32_t* evals, int32_t* queue,
+                 cudaStream_t st) {
+    if (max_rows == 0) return 0;
+    if (m.p < 1 || m.p > (size_t)kDynMaxCov) return fail(-2, "covariate columns must be in [1, 32]");
+    JXB_CUDA_OK(cudaMemsetAsync(queue, 0, sizeof(int32_t), st));
+    const ModelView mv = view_of(m);
+    // persistent warps: 2 CTAs x 8 warps per SM, never more warps than SNPs
+    const int sms = sm_count(m.device);
+    int blocks = (int)std::min<size_t>((size_t)sms * 2, (max_rows + 7) / 8);
+    if (blocks < 1) blocks = 1;
+#define S_STATIC(P) \
+    k3_launch_solve_p##P(mv, blocks, g_rot, ldc, (int)max_rows, n_rows_dev, sp, out, out_cols, evals, queue, st)
+#define S_DYN()                                                                                           \
+    solve_kernel<kDynMaxCov, true><<<blocks, 256, 0, st>>>(mv, g_rot, ldc, (int)max_rows, n_rows_dev, sp,  \
+                                                           out, out_cols, evals, queue)
+    JXB_DISPATCH_P((int)m.p, S_STATIC, S_DYN)
+#undef S_STATIC
+#undef S_DYN
+    JXB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_null_fit(const Model& m, int kind, double low, double high, int max_iter, double tol, int has_init,
+                    double init, double* out_dev, cudaStream_t st) {
+    if (m.p < 1 || m.p > (size_t)kDynMaxCov) return fail(-2, "covariate columns must be in [1, 32]");
+    const ModelView mv = view_of(m);
+#define N_STATIC(P) k3_launch_null_p##P(mv, kind, low, high, max_iter, tol, has_init, init, out_dev, st)
+#define N_DYN() null_kernel<kDynMaxCov, true><<<1, 32, 0, st>>>(mv, kind, low, high, max_iter, tol, has_init, init, out_dev)
+    JXB_DISPATCH_P((int)m.p, N_STATIC, N_DYN)
+#undef N_STATIC
+#undef N_DYN
+    JXB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_fixed_prepare(Model& m, double log10_lbd, cudaStream_t st) {
+    if (m.p < 1 || m.p > (size_t)kDynMaxCov) return fail(-2, "covariate columns must be in [1, 32]");
+    const ModelView mv = view_of(m);
+    const double lbd = pow(10.0, log10_lbd);
+    fixed_prepare_kernel<kDynMaxCov, true><<<1, 32, 0, st>>>(mv, lbd, m.fx_w, m.fx_py, m.fx_wx, m.fx_scal);
+    JXB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_fixed_solve(const Model& m, const float* g_rot, size_t ldc, size_t max_rows, const int32_t* n_rows_dev,
+                       int has_nullml, double nullml, double* out, int out_cols, cudaStream_t st) {
+    if (max_rows == 0) return 0;
+    const ModelView mv = view_of(m);
+    const int sms = sm_count(m.device);
+    int blocks = (int)std::min<size_t>((size_t)sms * 4, (max_rows + 7) / 8);
+    if (blocks < 1) blocks = 1;
+    fixed_solve_kernel<<<blocks, 256, 0, st>>>(mv, m.fx_w, m.fx_py, m.fx_wx, m.fx_scal, g_rot, ldc, (int)max_rows,
+                                               n_rows_dev, has_nullml, nullml, out, out_cols);
+    JXB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace jxb

@@ -1,0 +1,557 @@
+"""`janusx.janusx`-compatible function surface for the exact-LMM path, backed by libjxb200.so.
+
+Every function here keeps the name, argument order, defaults, return layout and error text of the
+reference PyO3 function it replaces (registered at src/lib.rs:911-941 of JanusX); the body is a thin
+ctypes call into the C ABI (include/jxb200.h).  `threads`, `rotate_block_rows` and `mmap_window_mb`
+are accepted for signature compatibility; they steer CPU thread pools / host tiling in the reference
+and have no meaning on the device path (rotate_block_rows is used as the device batch size hint by
+the file-level scans).
+
+The null model (S, Xcov, y_rot, U^T) is uploaded once per distinct set of arrays and kept resident in
+HBM (`DeviceModel`); the array-argument functions look the handle up in a small cache so a chunk loop
+that passes the same arrays every call -- exactly what python/janusx/pyBLUP/assoc.py does -- pays the
+U^T upload once.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import hashlib
+import math
+from collections import OrderedDict
+from typing import Callable, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _cabi
+from ._cabi import BedScanCfg, JxbError, QcCfg, SolveCfg, check, lib, ptr
+
+MODEL_CODES = {"add": 0, "dom": 1, "rec": 2, "het": 3}
+
+__all__ = [
+    "DeviceModel", "lmm_reml_chunk_f32", "lmm_reml_chunk_from_snp_f32", "lmm_reml_lmm2_chunk_from_snp_f32",
+    "lmm_assoc_chunk_f32", "lmm_assoc_chunk_from_snp_f32", "lmm_reml_null_f32", "ml_loglike_null_f32",
+    "lmm_rotate_x_y_with_ut_f64", "lmm_reml_assoc_bed_to_tsv_f32", "lmm_reml_lmm2_assoc_bed_to_tsv_f32",
+    "fvlmm_assoc_bed_to_tsv_f32", "fvlmm_assoc_chunk_f32", "fvlmm_assoc_chunk_from_snp_f32",
+]
+
+
+def _f64(a, name="array"):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+
+
+def _f32(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+
+
+def _model_code(genetic_model: str) -> int:
+    key = str(genetic_model).lower()
+    if key not in MODEL_CODES:
+        raise RuntimeError("model must be one of: add, dom, rec, het")
+    return MODEL_CODES[key]
+
+
+def _solve_cfg(low=-5.0, high=5.0, max_iter=30, tol=1e-2, init=None, nullml=None) -> SolveCfg:
+    c = SolveCfg()
+    c.low, c.high, c.tol, c.max_iter = float(low), float(high), float(tol), int(max_iter)
+    c.has_init = 0 if init is None else 1
+    c.init_log10_lbd = 0.0 if init is None else float(init)
+    c.has_nullml = 0 if nullml is None else 1
+    c.nullml = 0.0 if nullml is None else float(nullml)
+    return c
+
+
+class DeviceModel:
+    """The null model resident in HBM on one device (opaque jxb_model handle)."""
+
+    def __init__(self, s, xcov, y_rot, u_t=None, device: int = 0, u_t_on_device: bool = False):
+        _cabi.require_gpu()
+        self.s = _f64(s).reshape(-1)
+        self.xcov = _f64(xcov)
+        self.y = _f64(y_rot).reshape(-1)
+        n = self.y.shape[0]
+        if self.xcov.ndim != 2 or self.xcov.shape[0] != n:
+            raise RuntimeError("Xcov.n_rows must equal len(y_rot)")
+        if self.s.shape[0] != n:
+            raise RuntimeError("len(S) must equal len(y_rot)")
+        self.n, self.p = n, int(self.xcov.shape[1])
+        self.device = int(device)
+        self.has_ut = u_t is not None
+        h = C.c_void_p()
+        if u_t is not None and u_t_on_device:
+            # torch CUDA tensor (f32, contiguous, [n, n]) e.g. straight out of an NCCL broadcast
+            if tuple(u_t.shape) != (n, n):
+                raise RuntimeError("u_t must be (n, n) and row-major U^T")
+            import torch  # plumbing only
+
+            sd = torch.as_tensor(self.s, device=u_t.device)
+            xd = torch.as_tensor(self.xcov, device=u_t.device)
+            yd = torch.as_tensor(self.y, device=u_t.device)
+            check(lib().jxb_model_create_dev(self.device, n, self.p, ptr(sd), ptr(xd), ptr(yd), ptr(u_t), C.byref(h)))
+        else:
+            ut = None
+            if u_t is not None:
+                ut = _f32(u_t)
+                if ut.shape != (n, n):
+                    raise RuntimeError("u_t must be (n, n) and row-major U^T")
+            check(lib().jxb_model_create(self.device, n, self.p, ptr(self.s), ptr(self.xcov), ptr(self.y), ptr(ut),
+                                         C.byref(h)))
+        self._h = h
+
+    # -- lifetime ---------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().jxb_model_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        if not self._h:
+            raise JxbError("model is closed")
+        return self._h
+
+    def set_xy(self, xcov, y_rot):
+        xcov = _f64(xcov)
+        y = _f64(y_rot).reshape(-1)
+        if xcov.shape != (self.n, self.p) or y.shape[0] != self.n:
+            raise RuntimeError("Xcov.n_rows must equal len(y_rot)")
+        check(lib().jxb_model_set_xy(self.handle, ptr(xcov), ptr(y)))
+        self.xcov, self.y = xcov, y
+
+    def sync(self):
+        check(lib().jxb_model_sync(self.handle))
+
+    @property
+    def stream(self) -> int:
+        return int(lib().jxb_model_stream(self.handle) or 0)
+
+    # -- null model -------------------------------------------------------------------------------
+    def reml_null(self, low, high, max_iter=50, tol=1e-2) -> Tuple[float, float, float]:
+        if low >= high:
+            raise RuntimeError("low must be < high")
+        out = (C.c_double * 3)()
+        check(lib().jxb_reml_null(self.handle, low, high, int(max_iter), tol, out))
+        return float(out[0]), float(out[1]), float(out[2])
+
+    def ml_loglike_null(self, log10_lbd) -> float:
+        out = C.c_double()
+        check(lib().jxb_ml_loglike_null(self.handle, float(log10_lbd), C.byref(out)))
+        return float(out.value)
+
+    def ml_null(self, low, high, max_iter=30, tol=1e-2, init=None) -> Tuple[float, float]:
+        out = (C.c_double * 2)()
+        check(lib().jxb_ml_null(self.handle, low, high, int(max_iter), tol, 0 if init is None else 1,
+                                0.0 if init is None else float(init), out))
+        return float(out[0]), float(out[1])
+
+    def rotate_xy(self, x, y):
+        x = _f64(x)
+        y = _f64(y).reshape(-1)
+        xr = np.empty((self.n, x.shape[1]), dtype=np.float64)
+        yr = np.empty((self.n, 1), dtype=np.float64)
+        check(lib().jxb_rotate_xy(self.handle, ptr(x), x.shape[1], ptr(y), ptr(xr), ptr(yr)))
+        return xr, yr
+
+    # -- chunk scans ------------------------------------------------------------------------------
+    def _chunk_in(self, a, what):
+        a = _f32(a)
+        if a.ndim != 2 or a.shape[1] != self.n:
+            raise RuntimeError(f"{what} must be (m_chunk, n)")
+        return a
+
+    def lmm_reml_chunk(self, g, low, high, max_iter=50, tol=1e-2, nullml=None, rotated=True, init=None,
+                       return_evals=False):
+        g = self._chunk_in(g, "g_rot_chunk" if rotated else "snp_chunk")
+        if low >= high:
+            raise RuntimeError("low must be < high")
+        m = g.shape[0]
+        cfg = _solve_cfg(low, high, max_iter, tol, init, nullml)
+        out = np.zeros((m, 4 if nullml is not None else 3), dtype=np.float64)
+        ev = np.zeros(m, dtype=np.int32)
+        fn = lib().jxb_lmm_reml_chunk_f32 if rotated else lib().jxb_lmm_reml_chunk_from_snp_f32
+        check(fn(self.handle, ptr(g), m, C.byref(cfg), ptr(out), ptr(ev)))
+        return (out, ev) if return_evals else out
+
+    def lmm2_chunk(self, g, low, high, nullml, max_iter=50, tol=1e-2, rotated=False, init=None, return_evals=False):
+        g = self._chunk_in(g, "g_rot_chunk" if rotated else "snp_chunk")
+        if low >= high:
+            raise RuntimeError("low must be < high")
+        m = g.shape[0]
+        cfg = _solve_cfg(low, high, max_iter, tol, init, nullml)
+        out = np.zeros((m, 6), dtype=np.float64)
+        ev = np.zeros(m, dtype=np.int32)
+        check(lib().jxb_lmm2_chunk_f32(self.handle, ptr(g), m, 1 if rotated else 0, C.byref(cfg), ptr(out), ptr(ev)))
+        return (out, ev) if return_evals else out
+
+    def fixed_chunk(self, g, log10_lbd, nullml=None, rotated=False, return_meta=False):
+        g = self._chunk_in(g, "g_rot_chunk" if rotated else "snp_chunk")
+        if self.n <= self.p + 1:
+            raise RuntimeError("n must be > p_cov+1")
+        m = g.shape[0]
+        out = np.zeros((m, 4 if nullml is not None else 3), dtype=np.float64)
+        meta = (C.c_double * 3)()
+        nm = None if nullml is None else C.c_double(float(nullml))
+        check(lib().jxb_lmm_fixed_chunk_f32(self.handle, ptr(g), m, 1 if rotated else 0, float(log10_lbd),
+                                            C.byref(nm) if nm is not None else None, ptr(out), meta))
+        if return_meta:
+            return out, {"ypy": float(meta[0]), "log_det_v": float(meta[1]), "df": int(meta[2])}
+        return out
+
+    def rotate_block(self, snp, variant: int = 0) -> np.ndarray:
+        snp = self._chunk_in(snp, "snp_chunk")
+        out = np.empty_like(snp)
+        check(lib().jxb_rotate_block_f32(self.handle, ptr(snp), snp.shape[0], ptr(out), int(variant)))
+        return out
+
+    # -- packed scans -----------------------------------------------------------------------------
+    def decode_packed(self, packed, n_full, sample_idx=None, maf_thr=0.02, miss_thr=0.05, het_thr=1.0,
+                      genetic_model="add", want_g=True):
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        rows, bps = packed.shape
+        sidx = None if sample_idx is None else np.ascontiguousarray(sample_idx, dtype=np.int64)
+        qc = QcCfg(maf_thr, miss_thr, het_thr, _model_code(genetic_model))
+        counts = np.zeros((rows, 4), dtype=np.int32)
+        af = np.zeros(rows, dtype=np.float32)
+        mr = np.zeros(rows, dtype=np.float32)
+        nk = C.c_size_t()
+        g = np.zeros((rows, self.n), dtype=np.float32) if want_g else None
+        check(lib().jxb_decode_packed(self.handle, ptr(packed), bps, rows, int(n_full), ptr(sidx), C.byref(qc),
+                                      ptr(counts), ptr(af), ptr(mr), ptr(g), C.byref(nk)))
+        return counts, af, mr, (g[: nk.value] if want_g else None)
+
+    def scan_packed(self, packed, n_full, sample_idx=None, pre_keep=None, maf_thr=0.02, miss_thr=0.05, het_thr=1.0,
+                    genetic_model="add", mode="lmm", low=-5.0, high=5.0, max_iter=30, tol=1e-2, init=None,
+                    nullml=None, log10_lbd=None, return_evals=False):
+        """One batch of packed SNP rows -> (keep, af, missing, out[n_kept, cols])."""
+        packed = np.ascontiguousarray(packed, dtype=np.uint8) if isinstance(packed, np.ndarray) else packed
+        rows, bps = int(packed.shape[0]), int(packed.shape[1])
+        mode_i = {"lmm": 0, "lmm2": 1, "fvlmm": 2}[mode]
+        sidx = None if sample_idx is None else np.ascontiguousarray(sample_idx, dtype=np.int64)
+        pk = None if pre_keep is None else np.ascontiguousarray(pre_keep, dtype=np.uint8)
+        qc = QcCfg(maf_thr, miss_thr, het_thr, _model_code(genetic_model))
+        if mode_i == 2:
+            init = log10_lbd
+        cfg = _solve_cfg(low, high, max_iter, tol, init, nullml)
+        cols = 6 if mode_i == 1 else (4 if nullml is not None else 3)
+        keep = np.zeros(rows, dtype=np.uint8)
+        af = np.zeros(rows, dtype=np.float32)
+        missing = np.zeros(rows, dtype=np.int32)
+        out = np.zeros((rows, cols), dtype=np.float64)
+        ev = np.zeros(rows, dtype=np.int32)
+        nk = C.c_size_t()
+        check(lib().jxb_scan_packed(self.handle, ptr(packed), bps, rows, int(n_full), ptr(sidx), ptr(pk), C.byref(qc),
+                                    C.byref(cfg), mode_i, ptr(keep), ptr(af), ptr(missing), ptr(out), ptr(ev),
+                                    C.byref(nk)))
+        res = (keep.astype(bool), af, missing, out[: nk.value])
+        return res + (ev[: nk.value],) if return_evals else res
+
+    def scan_packed_dev(self, packed_dev_ptr: int, rows: int, bps: int, n_full: int, sample_idx_dev_ptr=None,
+                        maf_thr=0.02, miss_thr=0.05, het_thr=1.0, genetic_model="add", mode="lmm", low=-5.0,
+                        high=5.0, max_iter=30, tol=1e-2, init=None, nullml=None, log10_lbd=None):
+        """Asynchronous batch scan of packed rows already in HBM (results stay in the workspace)."""
+        mode_i = {"lmm": 0, "lmm2": 1, "fvlmm": 2}[mode]
+        qc = QcCfg(maf_thr, miss_thr, het_thr, _model_code(genetic_model))
+        if mode_i == 2:
+            init = log10_lbd
+        cfg = _solve_cfg(low, high, max_iter, tol, init, nullml)
+        check(lib().jxb_scan_packed_dev(self.handle, packed_dev_ptr, bps, rows, int(n_full), sample_idx_dev_ptr,
+                                        C.byref(qc), C.byref(cfg), mode_i))
+        return 6 if mode_i == 1 else (4 if nullml is not None else 3)
+
+    def scan_fetch(self, rows: int, cols: int):
+        keep = np.zeros(rows, dtype=np.uint8)
+        af = np.zeros(rows, dtype=np.float32)
+        missing = np.zeros(rows, dtype=np.int32)
+        out = np.zeros((rows, cols), dtype=np.float64)
+        ev = np.zeros(rows, dtype=np.int32)
+        nk = C.c_size_t()
+        check(lib().jxb_scan_fetch(self.handle, rows, cols, ptr(keep), ptr(af), ptr(missing), ptr(out), ptr(ev),
+                                   C.byref(nk)))
+        return keep.astype(bool), af, missing, out[: nk.value], ev[: nk.value]
+
+    def stage_ms(self):
+        ms = (C.c_float * 6)()
+        check(lib().jxb_last_stage_ms(self.handle, ms))
+        return dict(zip(("count_qc", "decode", "rotate", "solve", "h2d", "d2h"), [float(v) for v in ms]))
+
+    # -- file level -------------------------------------------------------------------------------
+    def scan_bed_to_tsv(self, bed_prefix, out_tsv, maf_thr, miss_thr, het_thr, genetic_model="add", snps_only=False,
+                        sample_ids=None, mode="lmm", low=-5.0, high=5.0, max_iter=30, tol=1e-2, nullml=None,
+                        init=None, log10_lbd=None, batch_rows=4096, progress_callback=None, progress_every=0,
+                        snp_begin=0, snp_end=0, write_header=True) -> int:
+        cfg = BedScanCfg()
+        cfg.bed_prefix = str(bed_prefix).encode()
+        cfg.out_tsv = str(out_tsv).encode()
+        cfg.qc = QcCfg(maf_thr, miss_thr, het_thr, _model_code(genetic_model))
+        mode_i = {"lmm": 0, "lmm2": 1, "fvlmm": 2}[mode]
+        if mode_i == 2:
+            init = log10_lbd
+        cfg.solve = _solve_cfg(low, high, max_iter, tol, init, nullml)
+        cfg.mode = mode_i
+        cfg.snps_only = 1 if snps_only else 0
+        keepalive = None
+        if sample_ids is not None:
+            ids = [str(x).encode() for x in sample_ids]
+            keepalive = (C.c_char_p * len(ids))(*ids)
+            cfg.sample_ids = keepalive
+            cfg.n_sample_ids = len(ids)
+        cfg.batch_rows = int(batch_rows)
+        cfg.snp_begin, cfg.snp_end = int(snp_begin), int(snp_end)
+        cfg.write_header = 1 if write_header else 0
+        cfg.progress_every = int(progress_every)
+        err = []
+
+        def _cb(done, total, _user):
+            if progress_callback is None:
+                return 0
+            try:
+                progress_callback(int(done), int(total))
+                return 0
+            except BaseException as ex:  # KeyboardInterrupt included: abort the scan, re-raise after
+                err.append(ex)
+                return 1
+
+        cb = _cabi.PROGRESS_CB(_cb)
+        rows = C.c_size_t()
+        rc = lib().jxb_scan_bed_to_tsv(self.handle, C.byref(cfg), C.byref(rows), cb, None)
+        if err:
+            raise err[0]
+        check(rc)
+        return int(rows.value)
+
+
+# ------------------------------------------------------------------------------------------------------
+# handle cache for the array-argument functions
+# ------------------------------------------------------------------------------------------------------
+_CACHE: "OrderedDict[tuple, DeviceModel]" = OrderedDict()
+_CACHE_MAX = 2
+
+
+def _digest(a: np.ndarray, sample: int = 1 << 16) -> bytes:
+    flat = a.reshape(-1)
+    if flat.shape[0] > sample:
+        step = flat.shape[0] // sample
+        flat = flat[::step]
+    return hashlib.blake2b(np.ascontiguousarray(flat).tobytes(), digest_size=12).digest()
+
+
+def _get_model(s, xcov, y_rot, u_t=None) -> DeviceModel:
+    s = _f64(s).reshape(-1)
+    xcov = _f64(xcov)
+    y = _f64(y_rot).reshape(-1)
+    n = y.shape[0]
+    if xcov.ndim != 2 or xcov.shape[0] != n:
+        raise RuntimeError("Xcov.n_rows must equal len(y_rot)")
+    if s.shape[0] != n:
+        raise RuntimeError("len(S) must equal len(y_rot)")
+    ut = None
+    if u_t is not None:
+        ut = np.asarray(u_t)
+        if ut.ndim != 2 or ut.shape != (n, n):
+            raise RuntimeError("u_t must be (n, n) and row-major U^T")
+    ut_key = None if ut is None else (ut.shape, str(ut.dtype), _digest(ut))
+    key_small = (n, xcov.shape[1], _digest(s, 1 << 30), _digest(xcov, 1 << 30), _digest(y, 1 << 30))
+    for key, mdl in list(_CACHE.items()):
+        if key[0] == key_small and (ut_key is None or key[1] == ut_key):
+            _CACHE.move_to_end(key)
+            return mdl
+    # same U^T, new trait/covariates: keep the resident U^T and swap the small arrays
+    if ut_key is not None:
+        for key, mdl in list(_CACHE.items()):
+            if key[1] == ut_key and key[0][0] == n and key[0][1] == xcov.shape[1] and key[0][2] == key_small[2]:
+                del _CACHE[key]
+                mdl.set_xy(xcov, y)
+                _CACHE[(key_small, ut_key)] = mdl
+                return mdl
+    mdl = DeviceModel(s, xcov, y, ut)
+    _CACHE[(key_small, ut_key)] = mdl
+    while len(_CACHE) > _CACHE_MAX:
+        _, old = _CACHE.popitem(last=False)
+        old.close()
+    return mdl
+
+
+def clear_model_cache() -> None:
+    while _CACHE:
+        _, m = _CACHE.popitem()
+        m.close()
+
+
+# ------------------------------------------------------------------------------------------------------
+# PyO3-compatible functions
+# ------------------------------------------------------------------------------------------------------
+def lmm_reml_chunk_f32(s, xcov, y_rot, low, high, g_rot_chunk, max_iter=50, tol=1e-2, threads=0, nullml=None):
+    """src/stats/lmm.rs:333-518 -> f64[m, 3|4] = beta, se, pwald[, plrt]."""
+    return _get_model(s, xcov, y_rot).lmm_reml_chunk(g_rot_chunk, low, high, max_iter, tol, nullml, rotated=True)
+
+
+def lmm_reml_chunk_from_snp_f32(s, xcov, y_rot, low, high, snp_chunk, u_t, max_iter=50, tol=1e-2, threads=0,
+                                nullml=None, rotate_block_rows=256):
+    """src/stats/lmm.rs:1479-1630."""
+    return _get_model(s, xcov, y_rot, u_t).lmm_reml_chunk(snp_chunk, low, high, max_iter, tol, nullml, rotated=False)
+
+
+def lmm_reml_lmm2_chunk_from_snp_f32(s, xcov, y_rot, low, high, snp_chunk, u_t, nullml, max_iter=50, tol=1e-2,
+                                     threads=0, rotate_block_rows=256):
+    """src/stats/lmm.rs:1632-1780 -> f64[m, 6] = beta, se, pwald, lambda_reml, ml_alt, plrt."""
+    return _get_model(s, xcov, y_rot, u_t).lmm2_chunk(snp_chunk, low, high, nullml, max_iter, tol, rotated=False)
+
+
+def lmm_assoc_chunk_f32(s, xcov, y_rot, log10_lbd, g_rot_chunk, threads=0, nullml=None):
+    """Fixed-lambda scan of a rotated block: src/stats/lmm.rs:2010-2223 / src/stats/fvlmm.rs:1691-1805."""
+    return _get_model(s, xcov, y_rot).fixed_chunk(g_rot_chunk, log10_lbd, nullml, rotated=True)
+
+
+def lmm_assoc_chunk_from_snp_f32(s, xcov, y_rot, log10_lbd, snp_chunk, u_t, threads=0, nullml=None):
+    """src/stats/lmm.rs:2225-2238."""
+    return _get_model(s, xcov, y_rot, u_t).fixed_chunk(snp_chunk, log10_lbd, nullml, rotated=False)
+
+
+fvlmm_assoc_chunk_f32 = lmm_assoc_chunk_f32
+fvlmm_assoc_chunk_from_snp_f32 = lmm_assoc_chunk_from_snp_f32
+
+
+def lmm_reml_null_f32(s, xcov, y_rot, low, high, max_iter=50, tol=1e-2):
+    """src/stats/reml.rs:570-616 -> (lambda, ml, reml)."""
+    if low >= high:
+        raise RuntimeError("low must be < high")
+    return _get_model(s, xcov, y_rot).reml_null(low, high, max_iter, tol)
+
+
+def ml_loglike_null_f32(s, xcov, y_rot, log10_lbd):
+    """src/stats/reml.rs:618-646."""
+    return _get_model(s, xcov, y_rot).ml_loglike_null(log10_lbd)
+
+
+def lmm_rotate_x_y_with_ut_f64(u_t, x, y, threads=0):
+    """src/stats/reml.rs:107-198 -> (f64[n, q], f64[n, 1])."""
+    y = _f64(y).reshape(-1)
+    n = y.shape[0]
+    if n == 0:
+        raise RuntimeError("y must not be empty")
+    x = _f64(x)
+    if x.ndim != 2:
+        raise RuntimeError("x must be 2D (n, q)")
+    if x.shape[0] != n:
+        raise RuntimeError(f"x rows must equal len(y): rows={x.shape[0]}, len(y)={n}")
+    ut = np.asarray(u_t)
+    if ut.ndim != 2:
+        raise RuntimeError("u_t must be 2D (n, n)")
+    if ut.shape != (n, n):
+        raise RuntimeError("u_t must be shape (n, n) and row-major U^T")
+    # the model only needs U^T here; S / Xcov / y are placeholders of the right shape
+    ut_key = (ut.shape, str(ut.dtype), _digest(ut))
+    for key, mdl in _CACHE.items():
+        if key[1] == ut_key:
+            return mdl.rotate_xy(x, y)
+    mdl = DeviceModel(np.ones(n), np.ones((n, 1)), np.zeros(n), ut)
+    _CACHE[((n, 1, b"rot", b"rot", _digest(y, 1 << 30)), ut_key)] = mdl
+    while len(_CACHE) > _CACHE_MAX:
+        _, old = _CACHE.popitem(last=False)
+        old.close()
+    return mdl.rotate_xy(x, y)
+
+
+def _check_bed_args(s, xcov, y_rot, u_t, low, high, tol):
+    if low >= high:
+        raise RuntimeError("low must be < high")
+    if not (math.isfinite(tol) and tol > 0.0):
+        raise RuntimeError("tol must be positive and finite")
+    y = np.asarray(y_rot).reshape(-1)
+    n = y.shape[0]
+    xc = np.asarray(xcov)
+    if xc.shape[0] != n:
+        raise RuntimeError("Xcov.n_rows must equal len(y_rot)")
+    if np.asarray(s).reshape(-1).shape[0] != n:
+        raise RuntimeError("len(S) must equal len(y_rot)")
+    if tuple(np.asarray(u_t).shape) != (n, n):
+        raise RuntimeError("u_t must be (n, n) row-major U^T")
+    if n <= xc.shape[1] + 1:
+        raise RuntimeError("n must be > p+1")
+
+
+def _reject_prepared(row_indices, row_flip, row_missing, row_maf):
+    given = [v is not None for v in (row_indices, row_flip, row_missing, row_maf)]
+    if any(given) and not all(given):
+        raise RuntimeError(
+            "prepared row metadata must provide all or none of: row_indices, row_flip, row_missing, row_maf")
+    if all(given):
+        raise NotImplementedError(
+            "prepared row metadata (row_indices/row_flip/row_missing/row_maf) is not supported yet: "
+            "the device path recomputes counts and QC from the packed rows")
+
+
+def lmm_reml_assoc_bed_to_tsv_f32(bed_prefix, out_tsv, s, xcov, y_rot, u_t, maf_thr, miss_thr, het_thr,
+                                  genetic_model="add", snps_only=False, sample_ids=None, row_indices=None,
+                                  row_flip=None, row_missing=None, row_maf=None, low=-5.0, high=5.0, max_iter=30,
+                                  tol=1e-2, threads=0, nullml=None, init_log10_lbd=None, rotate_block_rows=512,
+                                  progress_callback=None, progress_every=0, mmap_window_mb=None) -> int:
+    """src/stats/lmm.rs:2488-2750.  Warm start is never used (JX_LMM_UNIFIED_NO_WARM_START=1 semantics:
+    every SNP starts from the interval midpoint), so `init_log10_lbd` only matters for LMM2."""
+    _check_bed_args(s, xcov, y_rot, u_t, low, high, tol)
+    _model_code(genetic_model)
+    _reject_prepared(row_indices, row_flip, row_missing, row_maf)
+    mdl = _get_model(s, xcov, y_rot, u_t)
+    return mdl.scan_bed_to_tsv(bed_prefix, out_tsv, maf_thr, miss_thr, het_thr, genetic_model, snps_only, sample_ids,
+                               "lmm", low, high, max_iter, tol, nullml, None, None,
+                               batch_rows=max(int(rotate_block_rows), 4096), progress_callback=progress_callback,
+                               progress_every=progress_every)
+
+
+def lmm_reml_lmm2_assoc_bed_to_tsv_f32(bed_prefix, out_tsv, s, xcov, y_rot, u_t, maf_thr, miss_thr, het_thr,
+                                       genetic_model="add", snps_only=False, sample_ids=None, row_indices=None,
+                                       row_flip=None, row_missing=None, row_maf=None, low=-5.0, high=5.0,
+                                       max_iter=30, tol=1e-2, threads=0, nullml=None, init_log10_lbd_reml=None,
+                                       init_log10_lbd_ml=None, rotate_block_rows=512, progress_callback=None,
+                                       progress_every=0, mmap_window_mb=None) -> int:
+    """src/stats/lmm.rs:2753-3038 (REML start = init_reml.or(init_ml); ML start = per-SNP REML optimum)."""
+    _check_bed_args(s, xcov, y_rot, u_t, low, high, tol)
+    _model_code(genetic_model)
+    _reject_prepared(row_indices, row_flip, row_missing, row_maf)
+    if nullml is not None and not math.isfinite(nullml):
+        raise RuntimeError("nullml must be finite when provided")
+    mdl = _get_model(s, xcov, y_rot, u_t)
+
+    def _clamped(v):
+        if v is None or not math.isfinite(v):
+            return None
+        return min(max(float(v), low), high)
+
+    i_reml, i_ml = _clamped(init_log10_lbd_reml), _clamped(init_log10_lbd_ml)
+    if nullml is None:
+        _, nullml = mdl.ml_null(low, high, max_iter, tol, i_ml if i_ml is not None else i_reml)
+        if not math.isfinite(nullml):
+            raise RuntimeError("failed to optimize null ML for LMM2 unified scan")
+    init = i_reml if i_reml is not None else i_ml
+    return mdl.scan_bed_to_tsv(bed_prefix, out_tsv, maf_thr, miss_thr, het_thr, genetic_model, snps_only, sample_ids,
+                               "lmm2", low, high, max_iter, tol, nullml, init, None,
+                               batch_rows=max(int(rotate_block_rows), 4096), progress_callback=progress_callback,
+                               progress_every=progress_every)
+
+
+def fvlmm_assoc_bed_to_tsv_f32(bed_prefix, out_tsv, s, xcov, y_rot, log10_lbd, u_t, maf_thr, miss_thr, het_thr,
+                               genetic_model="add", snps_only=False, sample_ids=None, row_indices=None, row_flip=None,
+                               row_missing=None, row_maf=None, threads=0, nullml=None, rotate_block_rows=512,
+                               progress_callback=None, progress_every=0, mmap_window_mb=None):
+    """src/stats/fvlmm.rs:2482-3202 -> (rows_written, pve, log_det_v)."""
+    _check_bed_args(s, xcov, y_rot, u_t, -1.0, 1.0, 1e-2)
+    lbd = 10.0 ** float(log10_lbd)
+    if not (math.isfinite(lbd) and lbd > 0.0):
+        raise RuntimeError("invalid log10_lbd")
+    _model_code(genetic_model)
+    _reject_prepared(row_indices, row_flip, row_missing, row_maf)
+    mdl = _get_model(s, xcov, y_rot, u_t)
+    rows = mdl.scan_bed_to_tsv(bed_prefix, out_tsv, maf_thr, miss_thr, het_thr, genetic_model, snps_only, sample_ids,
+                               "fvlmm", nullml=nullml, log10_lbd=log10_lbd,
+                               batch_rows=max(int(rotate_block_rows), 4096), progress_callback=progress_callback,
+                               progress_every=progress_every)
+    # fvlmm.rs:2746-2753: pve = clamp(1 - ypy / sum y^2, 0, 1)
+    _, meta = mdl.fixed_chunk(np.zeros((1, mdl.n), dtype=np.float32), log10_lbd, rotated=True, return_meta=True)
+    y_sq = float(np.sum(mdl.y * mdl.y))
+    pve = float(min(max(1.0 - meta["ypy"] / y_sq, 0.0), 1.0)) if y_sq > 0.0 else float("nan")
+    return rows, pve, float(meta["log_det_v"])

@@ -1,0 +1,90 @@
+"""CPU-only checks of the drop-in boundary: the library loads, exports every declared symbol, refuses to
+compute without a GPU, and its host-side pieces (TSV formatter, argument validation) match the oracle."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+@pytest.fixture(scope="module")
+def cabi():
+    from janusx_b200 import _cabi
+    from janusx_b200 import build as jb
+    jb.build()
+    return _cabi
+
+
+def test_header_symbols_all_exported(cabi):
+    hdr = (ROOT / "include" / "jxb200.h").read_text()
+    declared = set(re.findall(r"\b(jxb_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    lib = C.CDLL(str(cabi.LIB_PATH))
+    missing = [n for n in sorted(declared) if not hasattr(lib, n)]
+    assert not missing, missing
+    assert declared == set(cabi.SYMBOLS), declared ^ set(cabi.SYMBOLS)
+    assert b"sm_100a" in cabi.lib().jxb_build_info()
+
+
+def test_no_cpu_fallback(cabi):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from janusx_b200 import jxrs
+    with pytest.raises(cabi.JxbError, match="no CPU fallback"):
+        jxrs.DeviceModel(np.ones(4), np.ones((4, 1)), np.zeros(4))
+    h = C.c_void_p()
+    s = np.ones(4)
+    rc = cabi.lib().jxb_model_create(0, 4, 1, s.ctypes.data, s.ctypes.data, s.ctypes.data, None, C.byref(h))
+    assert rc != 0 and b"no CPU fallback" in cabi.lib().jxb_last_error()
+
+
+def test_product_never_imports_oracle():
+    for path in (ROOT / "janusx_b200").rglob("*"):
+        if path.suffix in {".py", ".cu", ".cuh", ".cpp", ".h"}:
+            txt = path.read_text()
+            assert "oracle" not in txt.replace("oracle-free", ""), f"{path} mentions the oracle"
+
+
+def test_format_row_matches_oracle(cabi, oracle):
+    rng = np.random.default_rng(0)
+    rows = [
+        [0.5, 0.25, 6.1e-5], [float("nan"), float("nan"), 1.0], [1.0, 0.0, 0.3], [-3.25, 1e-3, 0.0],
+        [1.2345678, 0.5, 1e-320, 0.5], [0.1, 0.2, 0.3, 2.5, -1234.5678, 3e-300], [1e10, 1e-10, 1.0, float("nan"), float("inf"), 1.0],
+    ]
+    for _ in range(200):
+        k = int(rng.choice([3, 4, 6]))
+        rows.append(list(rng.normal(size=k) * 10.0 ** rng.integers(-8, 8, size=k)))
+    buf = C.create_string_buffer(4096)
+    for i, r in enumerate(rows):
+        a = np.ascontiguousarray(r, dtype=np.float64)
+        a[1] = abs(a[1]) if i % 5 else a[1]
+        a[2] = abs(a[2])
+        snp = "." if i % 3 == 0 else f"rs{i}"
+        af, mr = np.float32(rng.random()), np.float32(rng.random() * 0.1)
+        n = cabi.lib().jxb_format_row(buf, 4096, b"7", 1000 + i, snp.encode(), b"A", b"TG", af, mr,
+                                      a.ctypes.data_as(C.POINTER(C.c_double)), a.shape[0])
+        assert buf.raw[:n] == oracle.format_row("7", 1000 + i, snp, "A", "TG", float(af), float(mr), a), (i, r)
+
+
+def test_argument_validation_messages():
+    from janusx_b200 import jxrs
+    n = 8
+    s, x, y, ut = np.ones(n), np.ones((n, 2)), np.zeros(n), np.eye(n, dtype=np.float32)
+    with pytest.raises(RuntimeError, match="low must be < high"):
+        jxrs.lmm_reml_assoc_bed_to_tsv_f32("p", "o", s, x, y, ut, 0.02, 0.05, 1.0, low=1.0, high=1.0)
+    with pytest.raises(RuntimeError, match="tol must be positive and finite"):
+        jxrs.lmm_reml_assoc_bed_to_tsv_f32("p", "o", s, x, y, ut, 0.02, 0.05, 1.0, tol=0.0)
+    with pytest.raises(RuntimeError, match=r"u_t must be \(n, n\) row-major U\^T"):
+        jxrs.lmm_reml_assoc_bed_to_tsv_f32("p", "o", s, x, y, ut[:, :4], 0.02, 0.05, 1.0)
+    with pytest.raises(RuntimeError, match="model must be one of: add, dom, rec, het"):
+        jxrs.lmm_reml_assoc_bed_to_tsv_f32("p", "o", s, x, y, ut, 0.02, 0.05, 1.0, genetic_model="xyz")
+    with pytest.raises(RuntimeError, match="prepared row metadata must provide all or none"):
+        jxrs.lmm_reml_assoc_bed_to_tsv_f32("p", "o", s, x, y, ut, 0.02, 0.05, 1.0, row_indices=np.arange(3))
+    with pytest.raises(RuntimeError, match=r"x rows must equal len\(y\)"):
+        jxrs.lmm_rotate_x_y_with_ut_f64(ut, np.ones((n - 1, 2)), y)
+    with pytest.raises(RuntimeError, match="invalid log10_lbd"):
+        jxrs.fvlmm_assoc_bed_to_tsv_f32("p", "o", s, x, y, float("nan"), ut, 0.02, 0.05, 1.0)
