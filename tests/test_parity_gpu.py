@@ -1,0 +1,321 @@
+"""GPU parity tests: every call goes through the C ABI (libjxb200.so) and is compared with the CPU oracle.
+
+Tolerances are the north-star gates: counts / af / SNP order bit-exact; lambda 1e-6
+relative; beta, se 1e-8 relative; |delta(-log10 p)| <= 1e-6.  The rotated block is f32: the device sums
+in a different (tiled) order than the oracle's sequential-j loop, so an entry may land on the other side
+of an f32 rounding boundary -- allowed up to 1 ulp on a tiny fraction of entries.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from conftest import make_problem, null_model
+
+pytestmark = pytest.mark.gpu
+
+RTOL_BETA = 1e-8
+RTOL_LAMBDA = 1e-6
+ATOL_LOGP = 1e-6
+
+
+@pytest.fixture(scope="module")
+def jx():
+    from janusx_b200 import jxrs
+    yield jxrs
+    jxrs.clear_model_cache()
+
+
+def assert_results_close(got, want, cols_p=(2,), cols_lambda=(), cols_rel=(0, 1)):
+    assert got.shape == want.shape
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    ok = ~np.isnan(want[:, 0])
+    for c in cols_rel:
+        np.testing.assert_allclose(got[ok, c], want[ok, c], rtol=RTOL_BETA, atol=0)
+    for c in cols_lambda:
+        np.testing.assert_allclose(got[ok, c], want[ok, c], rtol=RTOL_LAMBDA, atol=0)
+    for c in cols_p:
+        assert np.max(np.abs(np.log10(got[:, c]) - np.log10(want[:, c]))) <= ATOL_LOGP
+
+
+def assert_rot_close(got, want):
+    diff = got != want
+    frac = diff.mean()
+    if frac > 0:
+        ulp = np.spacing(np.abs(want[diff]).astype(np.float32))
+        assert np.all(np.abs(got[diff] - want[diff]) <= ulp), "more than 1 f32 ulp"
+    assert frac < 1e-4, f"{frac:.2e} of rotated entries differ"
+
+
+def test_k1_counts_qc_decode_bit_exact(jx, oracle, golden_small):
+    G = golden_small
+    n = int(G["n"])
+    mdl = jx.DeviceModel(G["s"], G["xcov"], G["y"], np.ascontiguousarray(G["u"].T.astype(np.float32)))
+    counts, af, mr, g = mdl.decode_packed(G["packed"], n, None, 0.02, 0.05, 1.0)
+    assert np.array_equal(counts[:, 3].astype(bool), G["keep"])
+    assert np.array_equal(counts[:, 0], G["missing"])
+    assert np.array_equal(af.view(np.uint32), G["af"].view(np.uint32))
+    assert np.array_equal(mr.view(np.uint32), G["miss_rate"].view(np.uint32))
+    assert np.array_equal(g.view(np.uint32), G["g"].view(np.uint32))
+    # sample subset (gather path), golden + freshly computed oracle
+    sub = jx.DeviceModel(G["s"][: len(G["sidx"])], G["xcov"][: len(G["sidx"])], G["y"][: len(G["sidx"])])
+    c2, af2, _, g2 = sub.decode_packed(G["packed"], n, G["sidx"], 0.02, 0.05, 1.0)
+    assert np.array_equal(c2[:, 3].astype(bool), G["keep_s"]) and np.array_equal(c2[:, 0], G["missing_s"])
+    assert np.array_equal(af2.view(np.uint32), G["af_s"].view(np.uint32))
+    assert np.array_equal(g2.view(np.uint32), G["g_s"].view(np.uint32))
+
+
+@pytest.mark.parametrize("n,m,miss", [(1, 3, 0.0), (5, 7, 0.3), (33, 64, 0.1), (257, 40, 0.02), (1000, 300, 0.01)])
+def test_k1_ragged_shapes_and_models(jx, oracle, n, m, miss):
+    from janusx_b200 import synth
+    packed, _ = synth.draw_genotypes(m, n, seed=100 + n, missing_rate=miss)
+    packed[0] = 0  # monomorphic row
+    if m > 2:
+        packed[1] = 0b01010101  # all missing (padding bits included: must be masked)
+    mdl = jx.DeviceModel(np.ones(n), np.ones((n, 1)), np.zeros(n))
+    for model, thr in (("add", (0.0, 1.0, 1.0)), ("dom", (0.02, 0.5, 0.9)), ("rec", (0.0, 1.0, 0.0)), ("het", (0.1, 0.2, 1.0))):
+        keep, af, mr, missing = oracle.count_qc_block(packed, n, None, *thr)
+        counts, af_d, mr_d, g_d = mdl.decode_packed(packed, n, None, *thr, genetic_model=model)
+        assert np.array_equal(counts[:, 3].astype(bool), keep)
+        assert np.array_equal(counts[:, 0], missing)
+        assert np.array_equal(af_d.view(np.uint32), af.view(np.uint32))
+        assert np.array_equal(mr_d.view(np.uint32), mr.view(np.uint32))
+        idx = np.nonzero(keep)[0]
+        g = oracle.decode_centered_block(packed, n, af[idx], row_indices=idx, model=model)
+        assert g_d.shape == g.shape
+        assert np.array_equal(g_d.view(np.uint32), g.view(np.uint32))
+
+
+def test_k2_rotation_both_kernels(jx, oracle, golden_small):
+    G = golden_small
+    ut = np.ascontiguousarray(G["u"].T.astype(np.float32))
+    mdl = jx.DeviceModel(G["s"], G["xcov"], G["y"], ut)
+    for variant in (1, 0):
+        rot = mdl.rotate_block(G["g"], variant=variant)
+        assert_rot_close(rot, G["rot"])
+
+
+@pytest.mark.parametrize("n,rows", [(130, 5), (257, 129), (1000, 300)])
+def test_k2_rotation_edges(jx, oracle, n, rows):
+    rng = np.random.default_rng(n)
+    q, _ = np.linalg.qr(rng.normal(size=(n, n)))
+    ut = np.ascontiguousarray(q.T.astype(np.float32))
+    g = rng.normal(size=(rows, n)).astype(np.float32)
+    want = oracle.rotate_block(g, ut, mode=0)
+    mdl = jx.DeviceModel(np.ones(n), np.ones((n, 1)), np.zeros(n), ut)
+    assert_rot_close(mdl.rotate_block(g, variant=0), want)
+    assert_rot_close(mdl.rotate_block(g, variant=1), want)
+    # linearity (size-independent property): rot(a*g1 + g2) == a*rot(g1) + rot(g2) up to f32 rounding
+    g2 = rng.normal(size=(rows, n)).astype(np.float32)
+    lhs = mdl.rotate_block((2.0 * g + g2).astype(np.float32))
+    rhs = 2.0 * mdl.rotate_block(g) + mdl.rotate_block(g2)
+    assert np.allclose(lhs, rhs, rtol=0, atol=2e-5 * np.sqrt(n))
+
+
+def test_rotate_xy_and_null_fit(jx, oracle, golden_small):
+    G = golden_small
+    n = int(G["n"])
+    ut = np.ascontiguousarray(G["u"].T.astype(np.float32))
+    X = np.concatenate([np.ones((n, 1)), G["cov"]], axis=1)
+    xr, yr = jx.lmm_rotate_x_y_with_ut_f64(ut, X, G["y_raw"])
+    np.testing.assert_allclose(xr, G["xcov"], rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(yr[:, 0], G["y"], rtol=1e-12, atol=1e-13)
+    lbd, ml0, reml0 = jx.lmm_reml_null_f32(G["s"], G["xcov"], G["y"], -5.0, 5.0, 50, 1e-3)
+    assert math.isclose(lbd, G["null"][0], rel_tol=RTOL_LAMBDA)
+    assert math.isclose(ml0, G["null"][1], rel_tol=1e-10) and math.isclose(reml0, G["null"][2], rel_tol=1e-10)
+    assert math.isclose(jx.ml_loglike_null_f32(G["s"], G["xcov"], G["y"], 0.25),
+                        oracle.ml_loglike_null_f32(G["s"], G["xcov"], G["y"], 0.25), rel_tol=1e-12)
+    mdl = jx.DeviceModel(G["s"], G["xcov"], G["y"])
+    x_ml, ml_null = mdl.ml_null(float(G["bounds"][0]), float(G["bounds"][1]), 30, 1e-2)
+    assert math.isclose(x_ml, G["ml_null"][0], rel_tol=1e-6, abs_tol=1e-9)
+    assert math.isclose(ml_null, G["ml_null"][1], rel_tol=1e-10)
+
+
+def test_k3_solve_on_rotated_golden(jx, golden_small):
+    G = golden_small
+    lo, hi = map(float, G["bounds"])
+    out = jx.lmm_reml_chunk_f32(G["s"], G["xcov"], G["y"], lo, hi, G["rot"], 30, 1e-2)
+    assert_results_close(out, G["lmm"])
+    out4 = jx.lmm_reml_chunk_f32(G["s"], G["xcov"], G["y"], lo, hi, G["rot"], 30, 1e-2, nullml=float(G["null"][1]))
+    assert_results_close(out4, G["lmm4"], cols_p=(2, 3))
+    mdl = jx.DeviceModel(G["s"], G["xcov"], G["y"])
+    _, ev = mdl.lmm_reml_chunk(G["rot"], lo, hi, 30, 1e-2, return_evals=True)
+    assert np.array_equal(ev, G["lmm_evals"])   # same Brent path, evaluation for evaluation
+    out2 = mdl.lmm2_chunk(G["rot"], lo, hi, float(G["ml_null"][1]), 30, 1e-2, rotated=True)
+    assert_results_close(out2, G["lmm2"], cols_p=(2, 5), cols_lambda=(3,))
+    np.testing.assert_allclose(out2[:, 4], G["lmm2"][:, 4], rtol=1e-10)
+    fx, meta = mdl.fixed_chunk(G["rot"], float(np.log10(G["null"][0])), rotated=True, return_meta=True)
+    assert_results_close(fx, G["fixed"])
+    np.testing.assert_allclose([meta["ypy"], meta["log_det_v"], meta["df"]], G["fixed_meta"], rtol=1e-10)
+
+
+@pytest.mark.parametrize("p_cov", [1, 3, 5, 8, 11])
+def test_k3_covariate_counts(jx, oracle, p_cov):
+    # static register kernels for p<=8, runtime-p kernel above
+    case = make_problem(n=150, m=24, q=p_cov - 1, seed=40 + p_cov, missing_rate=0.01)
+    nm = null_model(oracle, case)
+    keep, af, _, _ = oracle.count_qc_block(case.packed, case.n, None, 0.0, 1.0, 1.0)
+    g = oracle.decode_centered_block(case.packed, case.n, af)
+    g[2] = 0.0   # degenerate SNP -> NaN, NaN, 1 (lmm.rs:121-125)
+    rot = oracle.rotate_block(g, nm["ut"])
+    want = oracle.lmm_reml_chunk_f32(case.s, nm["xcov"], nm["y"], nm["low"], nm["high"], rot, 30, 1e-2)
+    got = jx.lmm_reml_chunk_f32(case.s, nm["xcov"], nm["y"], nm["low"], nm["high"], rot, 30, 1e-2)
+    assert_results_close(got, want)
+    _, mlnull = oracle.lmm_ml_null_brent(case.s, nm["xcov"], nm["y"], nm["low"], nm["high"], 30, 1e-2)
+    want2 = oracle.lmm_reml_lmm2_chunk_f32(case.s, nm["xcov"], nm["y"], nm["low"], nm["high"], rot, mlnull, 30, 1e-2)
+    mdl = jx.DeviceModel(case.s, nm["xcov"], nm["y"])
+    got2 = mdl.lmm2_chunk(rot, nm["low"], nm["high"], mlnull, 30, 1e-2, rotated=True)
+    assert_results_close(got2, want2, cols_p=(2, 5), cols_lambda=(3,))
+
+
+def test_end_to_end_from_snp_and_packed(jx, oracle):
+    case = make_problem(n=400, m=600, q=3, seed=77, missing_rate=0.02)
+    nm = null_model(oracle, case)
+    n = case.n
+    keep, af, mr, missing = oracle.count_qc_block(case.packed, n, None, 0.02, 0.05, 1.0)
+    idx = np.nonzero(keep)[0]
+    g = oracle.decode_centered_block(case.packed, n, af[idx], row_indices=idx)
+    want = oracle.lmm_reml_chunk_from_snp_f32(case.s, nm["xcov"], nm["y"], nm["low"], nm["high"], g, nm["ut"], 30, 1e-2)
+    got = jx.lmm_reml_chunk_from_snp_f32(case.s, nm["xcov"], nm["y"], nm["low"], nm["high"], g, nm["ut"], 30, 1e-2)
+    assert_results_close(got, want)
+    # reference-faithful comparator: f32-accumulated rotation, the reference's own 1e-5 acceptance bound
+    ref32 = oracle.lmm_reml_chunk_from_snp_f32(case.s, nm["xcov"], nm["y"], nm["low"], nm["high"], g, nm["ut"], 30,
+                                               1e-2, rot_mode=1)
+    ok = ~np.isnan(ref32[:, 0])
+    rel = np.abs(got[ok, :2] - ref32[ok, :2]) / np.abs(ref32[ok, :2])
+    assert np.median(rel) < 1e-5
+    # packed scan = K1 -> K2 -> K3 in one call; chunking must not change results
+    mdl = jx.DeviceModel(case.s, nm["xcov"], nm["y"], nm["ut"])
+    k_d, af_d, miss_d, out_d, ev = mdl.scan_packed(case.packed, n, low=nm["low"], high=nm["high"], return_evals=True)
+    assert np.array_equal(k_d, keep) and np.array_equal(af_d.view(np.uint32), af.view(np.uint32))
+    assert np.array_equal(miss_d, missing)
+    assert_results_close(out_d, want)
+    parts = [mdl.scan_packed(case.packed[i:i + 128], n, low=nm["low"], high=nm["high"])[3] for i in range(0, 600, 128)]
+    assert np.array_equal(np.concatenate(parts), out_d, equal_nan=True)
+    # LMM2 and fixed-lambda through the same packed entry point
+    _, mlnull = oracle.lmm_ml_null_brent(case.s, nm["xcov"], nm["y"], nm["low"], nm["high"], 30, 1e-2)
+    want2 = oracle.lmm_reml_lmm2_chunk_from_snp_f32(case.s, nm["xcov"], nm["y"], nm["low"], nm["high"], g, nm["ut"],
+                                                    mlnull, 30, 1e-2)
+    out2 = mdl.scan_packed(case.packed, n, mode="lmm2", low=nm["low"], high=nm["high"], nullml=mlnull)[3]
+    assert_results_close(out2, want2, cols_p=(2, 5), cols_lambda=(3,))
+    l10 = float(np.log10(nm["lbd"]))
+    want3 = oracle.lmm_assoc_chunk_from_snp_f32(case.s, nm["xcov"], nm["y"], l10, g, nm["ut"])
+    out3 = mdl.scan_packed(case.packed, n, mode="fvlmm", log10_lbd=l10)[3]
+    assert_results_close(out3, want3)
+
+
+def test_sample_subset_scan(jx, oracle):
+    case = make_problem(n=300, m=120, q=2, seed=91, missing_rate=0.03)
+    sidx = np.array(sorted(np.random.default_rng(1).choice(300, size=211, replace=False)), dtype=np.int64)
+    import copy
+    sub = copy.copy(case)
+    # null model on the subset: recompute K on those samples
+    from janusx_b200 import synth
+    K = synth.vanraden_grm(case.packed, case.n)[np.ix_(sidx, sidx)]
+    K[np.diag_indices(len(sidx))] += 1e-6
+    s, u = np.linalg.eigh(K)
+    sub.s, sub.u, sub.n, sub.y, sub.cov = s, u, len(sidx), case.y[sidx], case.cov[sidx]
+    nm = null_model(oracle, sub)
+    keep, af, mr, missing = oracle.count_qc_block(case.packed, case.n, sidx, 0.02, 0.05, 1.0)
+    idx = np.nonzero(keep)[0]
+    g = oracle.decode_centered_block(case.packed, case.n, af[idx], sample_idx=sidx, row_indices=idx)
+    want = oracle.lmm_reml_chunk_from_snp_f32(s, nm["xcov"], nm["y"], nm["low"], nm["high"], g, nm["ut"], 30, 1e-2)
+    mdl = jx.DeviceModel(s, nm["xcov"], nm["y"], nm["ut"])
+    k_d, af_d, miss_d, out_d = mdl.scan_packed(case.packed, case.n, sample_idx=sidx, low=nm["low"], high=nm["high"])
+    assert np.array_equal(k_d, keep) and np.array_equal(af_d.view(np.uint32), af.view(np.uint32))
+    assert np.array_equal(miss_d, missing)
+    assert_results_close(out_d, want)
+
+
+def _tsv_fields(path):
+    lines = path.read_bytes().split(b"\n")
+    assert lines[-1] == b""
+    return lines[0], [l.split(b"\t") for l in lines[1:-1]]
+
+
+def _assert_tsv_equiv(got_path, want_path):
+    hg, rg = _tsv_fields(got_path)
+    hw, rw = _tsv_fields(want_path)
+    assert hg == hw and len(rg) == len(rw)
+    mismatched = 0
+    for a, b in zip(rg, rw):
+        assert a[:7] == b[:7]          # chrom pos snp alleles af miss: byte-exact
+        if a[7:] != b[7:]:
+            mismatched += 1
+            for x, y in zip(a[7:], b[7:]):   # a 4-decimal rounding boundary may flip the last digit
+                fx, fy = float(x), float(y)
+                assert (math.isnan(fx) and math.isnan(fy)) or math.isclose(fx, fy, rel_tol=2e-4, abs_tol=1.01e-4)
+    assert mismatched <= max(1, len(rw) // 200)
+
+
+def test_bed_to_tsv_matches_oracle(jx, oracle, tmp_path):
+    from janusx_b200 import synth
+    case = make_problem(n=320, m=900, q=2, seed=55, missing_rate=0.03)
+    nm = null_model(oracle, case)
+    prefix = str(tmp_path / "panel")
+    ids = [f"rs{i}" if i % 11 else "." for i in range(900)]
+    synth.write_plink(prefix, case.packed, case.n, snp_ids=ids)
+    args = (case.s, nm["xcov"], nm["y"], nm["ut"], 0.02, 0.05, 1.0)
+    seen = []
+    rows = jx.lmm_reml_assoc_bed_to_tsv_f32(prefix, str(tmp_path / "g.tsv"), *args, low=nm["low"], high=nm["high"],
+                                            rotate_block_rows=256, progress_callback=lambda d, t: seen.append((d, t)),
+                                            progress_every=300)
+    rows_o = oracle.scan_bed_to_tsv(prefix, str(tmp_path / "o.tsv"), *args, low=nm["low"], high=nm["high"])
+    assert rows == rows_o and rows > 0 and seen and seen[-1] == (900, 900)
+    _assert_tsv_equiv(tmp_path / "g.tsv", tmp_path / "o.tsv")
+    # LMM2 (null ML fitted inside, seeded like the CLI) and the fixed-lambda scan
+    l10 = float(np.log10(nm["lbd"]))
+    rows2 = jx.lmm_reml_lmm2_assoc_bed_to_tsv_f32(prefix, str(tmp_path / "g2.tsv"), *args, low=nm["low"],
+                                                  high=nm["high"], init_log10_lbd_reml=l10)
+    rows2_o = oracle.scan_bed_to_tsv(prefix, str(tmp_path / "o2.tsv"), *args, low=nm["low"], high=nm["high"],
+                                     model="lmm2", init_log10_lbd=l10)
+    assert rows2 == rows2_o
+    _assert_tsv_equiv(tmp_path / "g2.tsv", tmp_path / "o2.tsv")
+    rows3, pve, ldv = jx.fvlmm_assoc_bed_to_tsv_f32(prefix, str(tmp_path / "g3.tsv"), case.s, nm["xcov"], nm["y"], l10,
+                                                    nm["ut"], 0.02, 0.05, 1.0)
+    rows3_o = oracle.scan_bed_to_tsv(prefix, str(tmp_path / "o3.tsv"), *args, model="fvlmm", log10_lbd=l10)
+    assert rows3 == rows3_o and 0.0 <= pve <= 1.0 and math.isfinite(ldv)
+    _assert_tsv_equiv(tmp_path / "g3.tsv", tmp_path / "o3.tsv")
+    # sample subset by IID + snps_only + error paths
+    some = [f"S{j}" for j in range(case.n)]
+    with pytest.raises(RuntimeError, match="sample 'nobody' not found in PLINK FAM"):
+        jx.lmm_reml_assoc_bed_to_tsv_f32(prefix, str(tmp_path / "e.tsv"), *args, sample_ids=some[:-1] + ["nobody"])
+    (tmp_path / "bad.bed").write_bytes(b"\x00\x01\x02" + bytes(10))
+    (tmp_path / "bad.bim").write_text("")
+    (tmp_path / "bad.fam").write_text("".join(f"F S{j} 0 0 0 -9\n" for j in range(case.n)))
+    with pytest.raises(RuntimeError, match="only SNP-major BED supported"):
+        jx.lmm_reml_assoc_bed_to_tsv_f32(str(tmp_path / "bad"), str(tmp_path / "e.tsv"), *args)
+
+
+def test_model_objects_and_large_property_checks(jx, oracle):
+    """LMM/LMM2/FvLMM objects (pyBLUP/assoc.py interface) + size-independent properties at a larger n."""
+    from janusx_b200 import assoc, synth
+    case = make_problem(n=1500, m=256, q=3, seed=123, missing_rate=0.01)
+    n = case.n
+    K = case.u @ np.diag(case.s) @ case.u.T
+    K[np.diag_indices(n)] -= 1e-6
+    lmm = assoc.LMM(case.y, case.cov, K)
+    assert lmm.Dh.dtype == np.float32 and lmm.Xcov.shape == (n, 4) and lmm.y.shape == (n, 1)
+    keep, af, _, _ = oracle.count_qc_block(case.packed, n, None, 0.0, 1.0, 1.0)
+    g = oracle.decode_centered_block(case.packed, n, af)
+    res = lmm.gwas(g, threads=1)
+    assert res.shape == (256, 3) and np.all(np.isfinite(res))
+    # chunked == unchunked (python/janusx/assoc/smoke.py:45-46)
+    chunked = np.concatenate([lmm.gwas(g[i:i + 100], threads=2) for i in range(0, 256, 100)])
+    assert np.array_equal(res, chunked)
+    # oracle with the SAME spectral inputs the object holds
+    want = oracle.lmm_reml_chunk_from_snp_f32(lmm.S, lmm.Xcov, lmm.y[:, 0], lmm.bounds[0], lmm.bounds[1], g, lmm.Dh, 30, 1e-2)
+    assert_results_close(res, want)
+    # scaling a SNP by c scales beta and se by 1/c and leaves p unchanged (exact powers of two)
+    res_half = lmm.gwas((g * np.float32(0.5)).astype(np.float32))
+    np.testing.assert_allclose(res_half[:, :2], 2.0 * res[:, :2], rtol=1e-9)
+    assert np.max(np.abs(np.log10(res_half[:, 2]) - np.log10(res[:, 2]))) < 1e-8
+    lmm2 = assoc.LMM2.from_spectral(case.y, case.cov, lmm.S, case.u)
+    r2 = lmm2.gwas(g[:64])
+    assert r2.shape == (64, 6) and np.all(r2[:, 5] <= 1.0) and np.all(r2[:, 3] > 0)
+    np.testing.assert_allclose(r2[:, :2], res[:64, :2], rtol=1e-6)
+    fv = assoc.FvLMM.from_spectral(case.y, case.cov, lmm.S, case.u)
+    r3 = fv.gwas(g[:64])
+    assert r3.shape == (64, 3)
+    # fixed-lambda vs exact: same sign, similar magnitude for null SNPs
+    assert np.corrcoef(r3[:, 0], res[:64, 0])[0, 1] > 0.99
