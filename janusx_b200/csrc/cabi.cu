@@ -13,6 +13,7 @@ struct jxb_model {
     jxb::Model m;
     bool timing_ready = false;
     cudaEvent_t ev[8];
+    bool ev_rec[8] = {false, false, false, false, false, false, false, false};
     float stage_ms[6] = {0, 0, 0, 0, 0, 0};
     float* missr = nullptr;       // [cap_rows] device
     uint8_t* mask = nullptr;      // [cap_rows] device (pre-keep mask)
@@ -202,6 +203,7 @@ void tick(jxb_model* h, int i) {
         h->timing_ready = true;
     }
     cudaEventRecord(h->ev[i], h->m.stream);
+    h->ev_rec[i] = true;
 }
 
 SolveParams to_params(const jxb_solve_cfg* c, int mode) {
@@ -569,13 +571,19 @@ int jxb_scan_fetch(jxb_model* h, size_t rows, int out_cols, uint8_t* keep_host, 
     if (n_kept_host) *n_kept_host = (size_t)nk;
     if (g_timing && h->timing_ready) {
         for (int i = 0; i < 6; ++i) h->stage_ms[i] = 0.f;
-        float t;
-        if (cudaEventElapsedTime(&t, h->ev[1], h->ev[2]) == cudaSuccess) h->stage_ms[0] = t;
-        if (cudaEventElapsedTime(&t, h->ev[2], h->ev[3]) == cudaSuccess) h->stage_ms[1] = t;
-        if (cudaEventElapsedTime(&t, h->ev[3], h->ev[4]) == cudaSuccess) h->stage_ms[2] = t;
-        if (cudaEventElapsedTime(&t, h->ev[4], h->ev[5]) == cudaSuccess) h->stage_ms[3] = t;
-        if (cudaEventElapsedTime(&t, h->ev[0], h->ev[1]) == cudaSuccess) h->stage_ms[4] = t;
-        if (cudaEventElapsedTime(&t, h->ev[5], h->ev[6]) == cudaSuccess) h->stage_ms[5] = t;
+        auto span = [&](int a, int b) -> float {
+            float t = 0.f;
+            if (h->ev_rec[a] && h->ev_rec[b] && cudaEventElapsedTime(&t, h->ev[a], h->ev[b]) == cudaSuccess) return t;
+            (void)cudaGetLastError();  // an unrecorded pair must not poison later launch checks
+            return 0.f;
+        };
+        h->stage_ms[0] = span(1, 2);
+        h->stage_ms[1] = span(2, 3);
+        h->stage_ms[2] = span(3, 4);
+        h->stage_ms[3] = span(4, 5);
+        h->stage_ms[4] = span(0, 1);
+        h->stage_ms[5] = span(5, 6);
+        for (bool& r : h->ev_rec) r = false;
     }
     return 0;
 }

@@ -39,12 +39,17 @@ def assert_results_close(got, want, cols_p=(2,), cols_lambda=(), cols_rel=(0, 1)
 
 
 def assert_rot_close(got, want):
+    """f32-rounded f64 dot products: equal except where the two summation orders straddle an f32 rounding
+    boundary (<= 1 ulp), or where the entry is ~0 and f64 summation noise (~1e-13 of the row scale) exceeds
+    its ulp (centred genotypes projected on the near-constant eigenvector)."""
     diff = got != want
     frac = diff.mean()
     if frac > 0:
-        ulp = np.spacing(np.abs(want[diff]).astype(np.float32))
-        assert np.all(np.abs(got[diff] - want[diff]) <= ulp), "more than 1 f32 ulp"
-    assert frac < 1e-4, f"{frac:.2e} of rotated entries differ"
+        ulp = np.spacing(np.abs(want).astype(np.float32))
+        noise = 1e-13 * np.abs(want).max(axis=1, keepdims=True)
+        assert np.all(np.abs(got - want) <= ulp + noise), "beyond 1 f32 ulp + f64 summation noise"
+    big = np.abs(want) > 1e-6 * np.abs(want).max()
+    assert (diff & big).mean() < 1e-4, f"{(diff & big).mean():.2e} of rotated entries differ"
 
 
 def test_k1_counts_qc_decode_bit_exact(jx, oracle, golden_small):
