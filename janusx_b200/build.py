@@ -13,8 +13,9 @@ OUT = PKG / "libjxb200.so"
 # (source, object stem, extra defines).  k3_inst.cu is compiled once per static covariate count so the
 # heavy fully-unrolled K3 kernels build in parallel.
 UNITS = [("cabi.cu", "cabi", []), ("k1_decode.cu", "k1_decode", []), ("k2_rotate.cu", "k2_rotate", []),
-         ("k3_solve.cu", "k3_solve", []), ("bed_scan.cpp", "bed_scan", [])]
-UNITS += [("k3_inst.cu", f"k3_inst_p{p}", [f"-DJXB_P={p}"]) for p in range(1, 9)]
+         ("k3_solve.cu", "k3_solve", ["-fmad=false"]), ("bed_scan.cpp", "bed_scan", [])]
+# -fmad=false: K3 reproduces the reference's separate multiply/add rounding (Rust never fuses)
+UNITS += [("k3_inst.cu", f"k3_inst_p{p}", [f"-DJXB_P={p}", "-fmad=false"]) for p in range(1, 9)]
 SOURCES = sorted({u[0] for u in UNITS})
 HEADERS = [CSRC / "jxb_common.cuh", CSRC / "k3_solve.cuh", PKG.parent / "include" / "jxb200.h"]
 

@@ -153,6 +153,7 @@ int ensure_capacity(jxb_model* h, size_t rows, size_t bps, bool need_g) {
         if (m.packed) { cudaFree(m.packed); m.packed = nullptr; m.bps_cap = 0; }
         if (rc) return rc;
         m.cap_rows = cap;
+        m.ldr = cap;
     }
     if (need_g && !m.g64) {
         JXB_CUDA_OK(cudaMalloc((void**)&m.g64, m.cap_rows * m.ldk * sizeof(double)));
@@ -278,7 +279,7 @@ int chunk_common(jxb_model* h, const float* host, size_t rows, bool rotated, con
         rc = launch_widen_f32(m.stage_f32, n, rows, n, m.g64, m.ldk, m.stream);
         note_launch(1);
         if (rc) return rc;
-        rc = launch_rotate(m, rows, nullptr, m.stream, g_rotate_variant);
+        rc = launch_rotate(m, rows, nullptr, m.rot, m.ldc, 0, m.stream, g_rotate_variant);
         note_launch(1);
         if (rc) return rc;
     }
@@ -315,7 +316,7 @@ int scan_device_stages(jxb_model* h, const uint8_t* packed_dev, size_t bps, size
     note_launch(1);
     if (rc) return rc;
     tick(h, 3);
-    rc = launch_rotate(m, rows, m.n_kept, m.stream, g_rotate_variant);
+    rc = launch_rotate(m, rows, m.n_kept, m.rot, m.ldc, 0, m.stream, g_rotate_variant);
     note_launch(1);
     if (rc) return rc;
     tick(h, 4);
@@ -395,7 +396,7 @@ void jxb_model_destroy(jxb_model* h) {
     Model& m = h->m;
     cudaSetDevice(m.device);
     if (m.stream) cudaStreamSynchronize(m.stream);
-    void* ptrs[] = {m.s, m.y, m.xt, m.ut, m.g64, m.rot, m.out, m.evals, m.packed, m.counts, m.af, m.src_row,
+    void* ptrs[] = {m.s, m.y, m.xt, m.ut, m.g64, m.rot, m.rotT, m.out, m.evals, m.packed, m.counts, m.af, m.src_row,
                     m.n_kept, m.sample_idx, m.stage_f32, m.fx_w, m.fx_py, m.fx_wx, m.fx_scal, h->missr, h->mask,
                     h->scal};
     for (void* p : ptrs)
@@ -524,7 +525,7 @@ int jxb_rotate_block_f32(jxb_model* h, const float* snp, size_t rows, float* rot
     rc = launch_widen_f32(m.stage_f32, n, rows, n, m.g64, m.ldk, m.stream);
     note_launch(1);
     if (rc) return rc;
-    rc = launch_rotate(m, rows, nullptr, m.stream, variant);
+    rc = launch_rotate(m, rows, nullptr, m.rot, m.ldc, 0, m.stream, variant);
     note_launch(1);
     if (rc) return rc;
     JXB_CUDA_OK(cudaMemcpy2DAsync(rot_host, n * sizeof(float), m.rot, m.ldc * sizeof(float), n * sizeof(float), rows,

@@ -46,7 +46,9 @@ struct Model {
     // scan workspace (grown on demand)
     size_t cap_rows = 0;
     double* g64 = nullptr;     // [cap_rows_pad][ldk] decoded+centred genotypes (GEMM A operand)
-    float* rot = nullptr;      // [cap_rows][ldc]   rotated genotypes, f32 (reference storage type)
+    float* rotT = nullptr;     // [n][ldr]  rotated genotypes, f32 (reference storage type), SNP-minor for K3
+    size_t ldr = 0;            // = cap_rows
+    float* rot = nullptr;      // [cap_rows][ldc] row-major rotated block (only for jxb_rotate_block_f32), lazy
     size_t ldc = 0;
     double* out = nullptr;     // [cap_rows][8]
     int32_t* evals = nullptr;  // [cap_rows]
@@ -85,7 +87,11 @@ int launch_decode_center(const uint8_t* packed, size_t bps, const int32_t* src_r
                          double* g64, size_t ldk, float* g32, size_t ld32, cudaStream_t st);
 int launch_widen_f32(const float* src, size_t ld_src, size_t rows, size_t n, double* dst, size_t ldk,
                      cudaStream_t st);
-int launch_rotate(Model& m, size_t max_rows, const int32_t* n_rows_dev, cudaStream_t st, int variant);
+// out: transposed ? rotT-style [n][ld] : row-major [rows][ld]
+int launch_rotate(Model& m, size_t max_rows, const int32_t* n_rows_dev, float* out, size_t ld, int transposed,
+                  cudaStream_t st, int variant);
+int launch_transpose_f32(const float* src, size_t ld_src, size_t rows, size_t cols, float* dst, size_t ld_dst,
+                         cudaStream_t st);  // dst[c][r] = src[r][c]
 int launch_rotate_xy(const Model& m, const float* ut_f32, const double* x, size_t q, const double* y,
                      double* x_rot, double* y_rot, cudaStream_t st);
 int launch_solve(const Model& m, const float* g_rot, size_t ldc, size_t max_rows, const int32_t* n_rows_dev,

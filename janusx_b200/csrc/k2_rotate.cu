@@ -88,7 +88,7 @@ __device__ __forceinline__ void tile_coords(int tile, int mt_count, int nt_count
 
 __global__ void __launch_bounds__(THREADS, 1)
 rotate_dmma_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_ut,
-                   float* __restrict__ rot, size_t ldc, int n, int kblocks, int max_rows,
+                   float* __restrict__ rot, size_t ldc, int transposed, int n, int kblocks, int max_rows,
                    const int32_t* __restrict__ n_rows_dev) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -174,21 +174,37 @@ rotate_dmma_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_consta
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
 
-        // epilogue: round once to f32 (the reference's rotated-block storage type) and store
+        // epilogue: round once to f32 (the reference's rotated-block storage type) and store, either
+        // row-major [row][col] or SNP-minor [col][row] (what the per-SNP solve kernel reads coalesced)
         const int row0 = mt * BM + wm * 64 + g;
         const int col0 = nt * BN + wn * 32 + 2 * t;
+        if (transposed) {
 #pragma unroll
-        for (int mi = 0; mi < 8; ++mi) {
-            const int row = row0 + mi * 8;
-            if (row >= rows) continue;
-            float* dst = rot + (size_t)row * ldc;
+            for (int mi = 0; mi < 8; ++mi) {
+                const int row = row0 + mi * 8;
+                if (row >= rows) continue;
 #pragma unroll
-            for (int ni = 0; ni < 4; ++ni) {
-                const int col = col0 + ni * 8;
-                if (col + 1 < n) {
-                    *reinterpret_cast<float2*>(dst + col) = make_float2((float)acc[mi][ni][0], (float)acc[mi][ni][1]);
-                } else if (col < n) {
-                    dst[col] = (float)acc[mi][ni][0];
+                for (int ni = 0; ni < 4; ++ni) {
+                    const int col = col0 + ni * 8;
+                    if (col < n) rot[(size_t)col * ldc + row] = (float)acc[mi][ni][0];
+                    if (col + 1 < n) rot[(size_t)(col + 1) * ldc + row] = (float)acc[mi][ni][1];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int mi = 0; mi < 8; ++mi) {
+                const int row = row0 + mi * 8;
+                if (row >= rows) continue;
+                float* dst = rot + (size_t)row * ldc;
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) {
+                    const int col = col0 + ni * 8;
+                    if (col + 1 < n) {
+                        *reinterpret_cast<float2*>(dst + col) =
+                            make_float2((float)acc[mi][ni][0], (float)acc[mi][ni][1]);
+                    } else if (col < n) {
+                        dst[col] = (float)acc[mi][ni][0];
+                    }
                 }
             }
         }
@@ -199,7 +215,7 @@ rotate_dmma_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_consta
 // the variant used when tensor maps cannot be built.  64x64 tile, 16x16 threads, 4x4 outputs each.
 __global__ void __launch_bounds__(256) rotate_simple_kernel(const double* __restrict__ g64, size_t ldk,
                                                             const double* __restrict__ ut, float* __restrict__ rot,
-                                                            size_t ldc, int n, int max_rows,
+                                                            size_t ldc, int transposed, int n, int max_rows,
                                                             const int32_t* __restrict__ n_rows_dev) {
     __shared__ double sA[64][17];
     __shared__ double sB[64][17];
@@ -242,7 +258,7 @@ __global__ void __launch_bounds__(256) rotate_simple_kernel(const double* __rest
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int col = n0 + tx * 4 + j;
-            if (col < n) rot[(size_t)row * ldc + col] = (float)acc[i][j];
+            if (col < n) rot[transposed ? (size_t)col * ldc + row : (size_t)row * ldc + col] = (float)acc[i][j];
         }
     }
 }
@@ -271,6 +287,21 @@ __global__ void __launch_bounds__(256) rotate_xy_kernel(const double* __restrict
                 if (c < q) x_rot[(size_t)i * q + c] = acc; else y_rot[i] = acc;
             }
         }
+    }
+}
+
+__global__ void transpose_f32_kernel(const float* __restrict__ src, size_t ld_src, int rows, int cols,
+                                     float* __restrict__ dst, size_t ld_dst) {
+    __shared__ float tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+        const int r = r0 + k, c = c0 + threadIdx.x;
+        tile[k][threadIdx.x] = (r < rows && c < cols) ? src[(size_t)r * ld_src + c] : 0.0f;
+    }
+    __syncthreads();
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+        const int c = c0 + k, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) dst[(size_t)c * ld_dst + r] = tile[threadIdx.x][k];
     }
 }
 
@@ -315,12 +346,13 @@ int make_tensor_maps(Model& m) {
     return encode_f64_rows((CUtensorMap*)m.tmap_g, m.g64, round_up(m.cap_rows, BM), m.ldk, BM);
 }
 
-int launch_rotate(Model& m, size_t max_rows, const int32_t* n_rows_dev, cudaStream_t st, int variant) {
+int launch_rotate(Model& m, size_t max_rows, const int32_t* n_rows_dev, float* out, size_t ld, int transposed,
+                  cudaStream_t st, int variant) {
     if (max_rows == 0) return 0;
     if (!m.ut) return fail(-3, "model was created without U^T; rotation is unavailable");
     if (variant == 1) {
         dim3 grid((unsigned)((m.n + 63) / 64), (unsigned)((max_rows + 63) / 64));
-        rotate_simple_kernel<<<grid, 256, 0, st>>>(m.g64, m.ldk, m.ut, m.rot, m.ldc, (int)m.n, (int)max_rows,
+        rotate_simple_kernel<<<grid, 256, 0, st>>>(m.g64, m.ldk, m.ut, out, ld, transposed, (int)m.n, (int)max_rows,
                                                    n_rows_dev);
         JXB_CUDA_OK(cudaGetLastError());
         return 0;
@@ -340,7 +372,17 @@ int launch_rotate(Model& m, size_t max_rows, const int32_t* n_rows_dev, cudaStre
     const int grid = (int)std::min<size_t>((size_t)sms, tiles);
     const int kblocks = (int)(m.ldk / BK);
     rotate_dmma_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(*(const CUtensorMap*)m.tmap_g, *(const CUtensorMap*)m.tmap_ut,
-                                                          m.rot, m.ldc, (int)m.n, kblocks, (int)max_rows, n_rows_dev);
+                                                          out, ld, transposed, (int)m.n, kblocks, (int)max_rows,
+                                                          n_rows_dev);
+    JXB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_transpose_f32(const float* src, size_t ld_src, size_t rows, size_t cols, float* dst, size_t ld_dst,
+                         cudaStream_t st) {
+    if (rows == 0 || cols == 0) return 0;
+    dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32)), block(32, 8);
+    transpose_f32_kernel<<<grid, block, 0, st>>>(src, ld_src, (int)rows, (int)cols, dst, ld_dst);
     JXB_CUDA_OK(cudaGetLastError());
     return 0;
 }

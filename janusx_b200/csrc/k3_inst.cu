@@ -11,17 +11,32 @@
 
 namespace jxb {
 
-int JXB_CAT(k3_launch_solve_p, JXB_P)(const k3::ModelView& mv, int blocks, const float* g_rot, size_t ldc,
+int JXB_CAT(k3_launch_solve_p, JXB_P)(const k3::ModelView& mv, int blocks, const float* rot, size_t ldc,
                                       int max_rows, const int32_t* n_rows_dev, const SolveParams& sp, double* out,
                                       int out_cols, int32_t* evals, int32_t* queue, cudaStream_t st) {
-    k3::solve_kernel<JXB_P, false><<<blocks, 256, 0, st>>>(mv, g_rot, ldc, max_rows, n_rows_dev, sp, out, out_cols,
+    constexpr int kSmem = 8 * k3::WarpDims<JXB_P, true>::SMEM_DOUBLES * (int)sizeof(double);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k3::solve_warp_kernel<JXB_P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+        attr = true;
+    }
+    k3::solve_warp_kernel<JXB_P><<<blocks, 256, kSmem, st>>>(mv, rot, ldc, max_rows, n_rows_dev, sp, out, out_cols,
                                                             evals, queue);
     return 0;
 }
 
+int JXB_CAT(k3_solve_blocks_per_sm_p, JXB_P)() {
+    constexpr int kSmem = 8 * k3::WarpDims<JXB_P, true>::SMEM_DOUBLES * (int)sizeof(double);
+    int nb = 1;
+    cudaFuncSetAttribute(k3::solve_warp_kernel<JXB_P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k3::solve_warp_kernel<JXB_P>, 256, kSmem);
+    return nb < 1 ? 1 : nb;
+}
+
 int JXB_CAT(k3_launch_null_p, JXB_P)(const k3::ModelView& mv, int kind, double low, double high, int max_iter,
                                      double tol, int has_init, double init, double* out_dev, cudaStream_t st) {
-    k3::null_kernel<JXB_P, false><<<1, 32, 0, st>>>(mv, kind, low, high, max_iter, tol, has_init, init, out_dev);
+    constexpr int kSmem = k3::WarpDims<JXB_P, false>::SMEM_DOUBLES * (int)sizeof(double);
+    k3::null_warp_kernel<JXB_P><<<1, 32, kSmem, st>>>(mv, kind, low, high, max_iter, tol, has_init, init, out_dev);
     return 0;
 }
 

@@ -8,7 +8,8 @@ namespace jxb {
     int k3_launch_solve_p##P(const k3::ModelView&, int, const float*, size_t, int, const int32_t*,             \
                              const SolveParams&, double*, int, int32_t*, int32_t*, cudaStream_t);              \
     int k3_launch_null_p##P(const k3::ModelView&, int, double, double, int, double, int, double, double*,      \
-                            cudaStream_t);
+                            cudaStream_t);                                                                     \
+    int k3_solve_blocks_per_sm_p##P();
 JXB_DECL_P(1) JXB_DECL_P(2) JXB_DECL_P(3) JXB_DECL_P(4) JXB_DECL_P(5) JXB_DECL_P(6) JXB_DECL_P(7) JXB_DECL_P(8)
 #undef JXB_DECL_P
 
@@ -43,22 +44,39 @@ int sm_count(int device) {
         default: { CALL_DYN(); break; }           \
     }
 
-int launch_solve(const Model& m, const float* g_rot, size_t ldc, size_t max_rows, const int32_t* n_rows_dev,
+int launch_solve(const Model& m, const float* rot, size_t ldc, size_t max_rows, const int32_t* n_rows_dev,
                  const SolveParams& sp, double* out, int out_cols, int32_t* evals, int32_t* queue,
                  cudaStream_t st) {
     if (max_rows == 0) return 0;
     if (m.p < 1 || m.p > (size_t)kDynMaxCov) return fail(-2, "covariate columns must be in [1, 32]");
-    JXB_CUDA_OK(cudaMemsetAsync(queue, 0, sizeof(int32_t), st));
     const ModelView mv = view_of(m);
-    // persistent warps: 2 CTAs x 8 warps per SM, never more warps than SNPs
+    if (m.p > 8) {
+        // fallback: one thread per SNP
+        const int blocks = (int)((max_rows + 63) / 64);
+        solve_kernel<kDynMaxCov, true><<<blocks, 64, 0, st>>>(mv, rot, ldc, (int)max_rows, n_rows_dev, sp, out,
+                                                              out_cols, evals);
+        JXB_CUDA_OK(cudaGetLastError());
+        return 0;
+    }
+    JXB_CUDA_OK(cudaMemsetAsync(queue, 0, sizeof(int32_t), st));
+    int per_sm = 1;
+#define B_STATIC(P) per_sm = k3_solve_blocks_per_sm_p##P()
+#define B_DYN() per_sm = 1
+    static int per_sm_cache[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (per_sm_cache[m.p] == 0) {
+        JXB_DISPATCH_P((int)m.p, B_STATIC, B_DYN)
+        per_sm_cache[m.p] = per_sm;
+    }
+    per_sm = per_sm_cache[m.p];
+#undef B_STATIC
+#undef B_DYN
+    // persistent warps: fill every SM, never more warps than SNPs
     const int sms = sm_count(m.device);
-    int blocks = (int)std::min<size_t>((size_t)sms * 2, (max_rows + 7) / 8);
+    int blocks = (int)std::min<size_t>((size_t)sms * per_sm, (max_rows + 7) / 8);
     if (blocks < 1) blocks = 1;
 #define S_STATIC(P) \
-    k3_launch_solve_p##P(mv, blocks, g_rot, ldc, (int)max_rows, n_rows_dev, sp, out, out_cols, evals, queue, st)
-#define S_DYN()                                                                                           \
-    solve_kernel<kDynMaxCov, true><<<blocks, 256, 0, st>>>(mv, g_rot, ldc, (int)max_rows, n_rows_dev, sp,  \
-                                                           out, out_cols, evals, queue)
+    k3_launch_solve_p##P(mv, blocks, rot, ldc, (int)max_rows, n_rows_dev, sp, out, out_cols, evals, queue, st)
+#define S_DYN() (void)0
     JXB_DISPATCH_P((int)m.p, S_STATIC, S_DYN)
 #undef S_STATIC
 #undef S_DYN
@@ -83,20 +101,27 @@ int launch_fixed_prepare(Model& m, double log10_lbd, cudaStream_t st) {
     if (m.p < 1 || m.p > (size_t)kDynMaxCov) return fail(-2, "covariate columns must be in [1, 32]");
     const ModelView mv = view_of(m);
     const double lbd = pow(10.0, log10_lbd);
-    fixed_prepare_kernel<kDynMaxCov, true><<<1, 32, 0, st>>>(mv, lbd, m.fx_w, m.fx_py, m.fx_wx, m.fx_scal);
+    fixed_prepare_kernel<<<1, 32, 0, st>>>(mv, lbd, m.fx_w, m.fx_py, m.fx_wx, m.fx_scal);
     JXB_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-int launch_fixed_solve(const Model& m, const float* g_rot, size_t ldc, size_t max_rows, const int32_t* n_rows_dev,
+int launch_fixed_solve(const Model& m, const float* rot, size_t ldc, size_t max_rows, const int32_t* n_rows_dev,
                        int has_nullml, double nullml, double* out, int out_cols, cudaStream_t st) {
     if (max_rows == 0) return 0;
+    if (m.p > 30) return fail(-2, "fixed-lambda scan supports at most 30 covariate columns");
     const ModelView mv = view_of(m);
+    const int smem = 8 * 32 * 33 * (int)sizeof(double);
+    static bool attr = false;
+    if (!attr) {
+        JXB_CUDA_OK(cudaFuncSetAttribute(fixed_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr = true;
+    }
     const int sms = sm_count(m.device);
-    int blocks = (int)std::min<size_t>((size_t)sms * 4, (max_rows + 7) / 8);
+    int blocks = (int)std::min<size_t>((size_t)sms * 3, (max_rows + 7) / 8);
     if (blocks < 1) blocks = 1;
-    fixed_solve_kernel<<<blocks, 256, 0, st>>>(mv, m.fx_w, m.fx_py, m.fx_wx, m.fx_scal, g_rot, ldc, (int)max_rows,
-                                               n_rows_dev, has_nullml, nullml, out, out_cols);
+    fixed_solve_kernel<<<blocks, 256, smem, st>>>(mv, m.fx_w, m.fx_py, m.fx_wx, m.fx_scal, rot, ldc, (int)max_rows,
+                                                  n_rows_dev, has_nullml, nullml, out, out_cols);
     JXB_CUDA_OK(cudaGetLastError());
     return 0;
 }
