@@ -14,7 +14,7 @@ namespace jxb {
 int JXB_CAT(k3_launch_solve_p, JXB_P)(const k3::ModelView& mv, int blocks, const float* rot, size_t ldc,
                                       int max_rows, const int32_t* n_rows_dev, const SolveParams& sp, double* out,
                                       int out_cols, int32_t* evals, int32_t* queue, cudaStream_t st) {
-    constexpr int kSmem = 8 * k3::WarpDims<JXB_P, true>::SMEM_DOUBLES * (int)sizeof(double);
+    constexpr int kSmem = 8 * 2 * k3::WarpDims<JXB_P, true>::SMEM_DOUBLES * (int)sizeof(double);
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(k3::solve_warp_kernel<JXB_P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
@@ -26,7 +26,7 @@ int JXB_CAT(k3_launch_solve_p, JXB_P)(const k3::ModelView& mv, int blocks, const
 }
 
 int JXB_CAT(k3_solve_blocks_per_sm_p, JXB_P)() {
-    constexpr int kSmem = 8 * k3::WarpDims<JXB_P, true>::SMEM_DOUBLES * (int)sizeof(double);
+    constexpr int kSmem = 8 * 2 * k3::WarpDims<JXB_P, true>::SMEM_DOUBLES * (int)sizeof(double);
     int nb = 1;
     cudaFuncSetAttribute(k3::solve_warp_kernel<JXB_P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k3::solve_warp_kernel<JXB_P>, 256, kSmem);
@@ -35,7 +35,7 @@ int JXB_CAT(k3_solve_blocks_per_sm_p, JXB_P)() {
 
 int JXB_CAT(k3_launch_null_p, JXB_P)(const k3::ModelView& mv, int kind, double low, double high, int max_iter,
                                      double tol, int has_init, double init, double* out_dev, cudaStream_t st) {
-    constexpr int kSmem = k3::WarpDims<JXB_P, false>::SMEM_DOUBLES * (int)sizeof(double);
+    constexpr int kSmem = 2 * k3::WarpDims<JXB_P, false>::SMEM_DOUBLES * (int)sizeof(double);
     k3::null_warp_kernel<JXB_P><<<1, 32, kSmem, st>>>(mv, kind, low, high, max_iter, tol, has_init, init, out_dev);
     return 0;
 }
