@@ -12,7 +12,7 @@ CSRC = PKG / "csrc"
 OUT = PKG / "libjxb200.so"
 # (source, object stem, extra defines).  k3_inst.cu is compiled once per static covariate count so the
 # heavy fully-unrolled K3 kernels build in parallel.
-UNITS = [("cabi.cu", "cabi", []), ("k1_decode.cu", "k1_decode", []), ("k2_rotate.cu", "k2_rotate", []),
+UNITS = [("cabi.cu", "cabi", []), ("k1_decode.cu", "k1_decode", []), ("k2_rotate.cu", "k2_rotate", []), ("k2_int8.cu", "k2_int8", []),
          ("k3_solve.cu", "k3_solve", ["-fmad=false"]), ("bed_scan.cpp", "bed_scan", [])]
 # -fmad=false: K3 reproduces the reference's separate multiply/add rounding (Rust never fuses)
 UNITS += [("k3_inst.cu", f"k3_inst_p{p}", [f"-DJXB_P={p}", "-fmad=false"]) for p in range(1, 9)]
@@ -72,7 +72,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             sys.stderr.write(f"--- nvcc {src} ---\n{out}\n")
     if failed:
         raise RuntimeError("nvcc compilation failed")
-    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", ccbin, "-o", str(OUT), *objs, "-lcudart", "-lpthread"]
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", ccbin, "-o", str(OUT), *objs, "-lcudart", "-lpthread", "-ldl"]
     subprocess.run(link, check=True, env=env)
     return OUT
 

@@ -311,14 +311,33 @@ int scan_device_stages(jxb_model* h, const uint8_t* packed_dev, size_t bps, size
     note_launch(1);
     if (rc) return rc;
     tick(h, 2);
-    rc = launch_decode_center(packed_dev, bps, m.src_row, m.n_kept, rows, n_full, sidx_dev, m.n, m.af, m.counts,
-                              qc->genetic_model, m.g64, m.ldk, nullptr, 0, m.stream);
-    note_launch(1);
-    if (rc) return rc;
-    tick(h, 3);
-    rc = launch_rotate(m, rows, m.n_kept, m.rot, m.ldc, 0, m.stream, g_rotate_variant);
-    note_launch(1);
-    if (rc) return rc;
+    if (g_rotate_variant == 2 && qc->genetic_model == JXB_MODEL_ADD) {
+        // int8-sliced exact rotation (k2_int8.cu): int8 operands instead of the f64 block (additive coding
+        // only: for dom/rec/het the T_2 coefficient is O(1) and the DMMA path is used)
+        rc = prepare_int8_slices(m, m.stream);
+        if (rc) return rc;
+        rc = ensure_int8_workspace(m, m.cap_rows);
+        if (rc) return rc;
+        rc = launch_decode_int8(m, packed_dev, bps, m.src_row, m.n_kept, rows, n_full, sidx_dev, m.af, m.counts,
+                                qc->genetic_model, m.stream);
+        if (rc) return rc;
+        tick(h, 3);
+        int32_t nk = 0, anym = 0;
+        JXB_CUDA_OK(cudaMemcpyAsync(&nk, m.n_kept, sizeof nk, cudaMemcpyDeviceToHost, m.stream));
+        JXB_CUDA_OK(cudaMemcpyAsync(&anym, m.flags8, sizeof anym, cudaMemcpyDeviceToHost, m.stream));
+        JXB_CUDA_OK(cudaStreamSynchronize(m.stream));
+        rc = launch_rotate_int8_lib(m, (size_t)nk, anym != 0, m.stream);
+        if (rc) return rc;
+    } else {
+        rc = launch_decode_center(packed_dev, bps, m.src_row, m.n_kept, rows, n_full, sidx_dev, m.n, m.af, m.counts,
+                                  qc->genetic_model, m.g64, m.ldk, nullptr, 0, m.stream);
+        note_launch(1);
+        if (rc) return rc;
+        tick(h, 3);
+        rc = launch_rotate(m, rows, m.n_kept, m.rot, m.ldc, 0, m.stream, g_rotate_variant == 2 ? 0 : g_rotate_variant);
+        note_launch(1);
+        if (rc) return rc;
+    }
     tick(h, 4);
     rc = run_solve(h, rows, m.n_kept, cfg, mode);
     if (rc) return rc;
@@ -398,7 +417,7 @@ void jxb_model_destroy(jxb_model* h) {
     if (m.stream) cudaStreamSynchronize(m.stream);
     void* ptrs[] = {m.s, m.y, m.xt, m.ut, m.g64, m.rot, m.rotT, m.out, m.evals, m.packed, m.counts, m.af, m.src_row,
                     m.n_kept, m.sample_idx, m.stage_f32, m.fx_w, m.fx_py, m.fx_wx, m.fx_scal, h->missr, h->mask,
-                    h->scal};
+                    h->scal, m.q8, m.q8_inv_scale, m.q8_rk, m.a8, m.coef, m.flags8, m.c32, m.lt_ws};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->timing_ready)

@@ -63,6 +63,14 @@ struct Model {
     void* tmap_ut = nullptr;   // CUtensorMap for ut (host copy, 128 B)
     void* tmap_g = nullptr;    // CUtensorMap for g64
     cudaStream_t stream = nullptr;
+    // int8-sliced rotation (k2_int8.cu)
+    int8_t* q8 = nullptr; size_t ld8 = 0, q8_rows = 0;   // 7 digit planes [q8_rows][ld8]
+    double* q8_inv_scale = nullptr; double* q8_rk = nullptr;
+    int8_t* a8 = nullptr; size_t a8_rows = 0;            // 3 operand planes [a8_rows][ld8]: dosage, hom, missing
+    double* coef = nullptr;                              // [a8_rows][4]
+    int32_t* flags8 = nullptr;                           // [0] = any missing call in the batch
+    int32_t* c32 = nullptr; size_t c32_elems = 0;        // int32 slice results (library variant)
+    void* lt_ws = nullptr; size_t lt_ws_bytes = 0;
     // fixed-lambda cache (A14)
     float* fx_w = nullptr; float* fx_py = nullptr; float* fx_wx = nullptr; double* fx_scal = nullptr;
     double fx_log10_lbd = 0.0; bool fx_valid = false;
@@ -105,5 +113,12 @@ int launch_fixed_solve(const Model& m, const float* g_rot, size_t ldc, size_t ma
                        const int32_t* n_rows_dev, int has_nullml, double nullml, double* out, int out_cols,
                        cudaStream_t st);
 int make_tensor_maps(Model& m);
+// int8-sliced exact rotation (k2_int8.cu)
+int prepare_int8_slices(Model& m, cudaStream_t st);
+int ensure_int8_workspace(Model& m, size_t rows_cap);
+int launch_decode_int8(Model& m, const uint8_t* packed, size_t bps, const int32_t* src_row, const int32_t* n_kept,
+                       size_t max_rows, size_t n_full, const int64_t* sample_idx, const float* af_by_src,
+                       const int32_t* counts_by_src, int model_code, cudaStream_t st);
+int launch_rotate_int8_lib(Model& m, size_t rows, bool has_missing, cudaStream_t st);
 
 }  // namespace jxb

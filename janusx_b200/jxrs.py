@@ -376,6 +376,12 @@ def _get_model(s, xcov, y_rot, u_t=None) -> DeviceModel:
     return mdl
 
 
+def set_rotate_variant(variant: int) -> None:
+    """Rotation kernel used by the packed scans: 0 = FP64 DMMA/TMA GEMM (default), 1 = CUDA-core cross-check,
+    2 = exact int8-sliced tensor-core rotation (additive coding; see csrc/k2_int8.cu)."""
+    lib().jxb_set_rotate_variant(int(variant))
+
+
 def clear_model_cache() -> None:
     while _CACHE:
         _, m = _CACHE.popitem()

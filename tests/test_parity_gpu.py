@@ -326,3 +326,36 @@ def test_model_objects_and_large_property_checks(jx, oracle):
     assert r3.shape == (64, 3)
     # fixed-lambda vs exact: same sign, similar magnitude for null SNPs
     assert np.corrcoef(r3[:, 0], res[:64, 0])[0, 1] > 0.99
+
+
+def test_int8_sliced_rotation_variant(jx, oracle):
+    """variant 2: exact int8-sliced tensor-core rotation must satisfy the same gates as the DMMA path
+    (with and without missing calls, identity and subset samples)."""
+    try:
+        for miss, seed in ((0.0, 301), (0.03, 302)):
+            case = make_problem(n=520, m=700, q=3, seed=seed, missing_rate=miss)
+            nm = null_model(oracle, case)
+            n = case.n
+            keep, af, mr, missing = oracle.count_qc_block(case.packed, n, None, 0.02, 0.05, 1.0)
+            idx = np.nonzero(keep)[0]
+            g = oracle.decode_centered_block(case.packed, n, af[idx], row_indices=idx)
+            want = oracle.lmm_reml_chunk_from_snp_f32(case.s, nm["xcov"], nm["y"], nm["low"], nm["high"], g, nm["ut"], 30, 1e-2)
+            mdl = jx.DeviceModel(case.s, nm["xcov"], nm["y"], nm["ut"])
+            jx.set_rotate_variant(2)
+            k2, af2, ms2, out2 = mdl.scan_packed(case.packed, n, low=nm["low"], high=nm["high"])
+            jx.set_rotate_variant(0)
+            k0, af0, ms0, out0 = mdl.scan_packed(case.packed, n, low=nm["low"], high=nm["high"])
+            assert np.array_equal(k2, keep) and np.array_equal(ms2, missing)
+            assert_results_close(out2, want)
+            assert_results_close(out2, out0)
+            # chunking invariance with the int8 path
+            jx.set_rotate_variant(2)
+            parts = [mdl.scan_packed(case.packed[i:i + 300], n, low=nm["low"], high=nm["high"])[3] for i in range(0, 700, 300)]
+            assert np.array_equal(np.concatenate(parts), out2, equal_nan=True)
+            # non-additive coding falls back to the DMMA kernel
+            d2 = mdl.scan_packed(case.packed, n, low=nm["low"], high=nm["high"], genetic_model="dom")[3]
+            jx.set_rotate_variant(0)
+            d0 = mdl.scan_packed(case.packed, n, low=nm["low"], high=nm["high"], genetic_model="dom")[3]
+            assert np.array_equal(d2, d0, equal_nan=True)
+    finally:
+        jx.set_rotate_variant(0)
