@@ -41,7 +41,8 @@ def parse_args():
     ap.add_argument("--grm-snps", type=int, default=int(os.environ.get("JXB_BENCH_GRM_SNPS", 50000)))
     ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("JXB_BENCH_CPU_SAMPLE", 1024)))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--rotate-variant", type=int, default=0)
+    ap.add_argument("--rotate-variant", type=int, default=int(os.environ.get("JXB_BENCH_ROTATE", 2)),
+                    help="0 = FP64 DMMA GEMM, 2 = exact int8-sliced tensor-core rotation (default)")
     return ap.parse_args()
 
 
@@ -357,28 +358,41 @@ def main():
 
     if rank == 0:
         rot_s = st["rotate"] * 1e-3
-        achieved = 2.0 * n * n * kept / rot_s / 1e12 if rot_s > 0 else 0.0
+        rot_flop = 2.0 * n * n * kept                      # FP64-equivalent work of the rotation
         d = p + 1
-        solve_flop = mean_evals * n * (3 * d * (d + 1) / 2 + 5 * d + 3) * kept
+        flop_per_eval = n * (3 * d * (d + 1) / 2 + 5 * d + 3 + 2)   # + 1 divide + 1 log per sample
+        solve_flop = mean_evals * flop_per_eval * kept
+        solve_s = st["solve"] * 1e-3
+        fp64_core_peak = 36.0      # TFLOP/s: 18.0 T DFMA/s measured with tools/fp64_probe.cu (profiles/r1_fp64_probe.txt)
+        rot_roof = {"kernel": ("rotate_dmma_kernel (FP64 DMMA GEMM)" if args.rotate_variant == 0 else
+                               "int8-sliced exact rotation (10 slice GEMMs + recombine_kernel)"),
+                    "bound": "tensor", "achieved": rot_flop / rot_s / 1e12 if rot_s > 0 else 0.0, "peak": fp64_peak,
+                    "unit": "TFLOP/s (FP64-equivalent)", "frac": (rot_flop / rot_s / 1e12 / fp64_peak) if rot_s > 0 and fp64_peak > 0 else None,
+                    "traffic": None, "launch_ms": st["rotate"],
+                    "peak_source": "cuBLAS DGEMM (M=4096,N=K=n) measured in this run; MEASURED_PEAKS.json holds no FP64 "
+                                   "figure. frac > 1 for the int8-sliced variant: same f64-accurate result from 10 exact "
+                                   "int8 slice GEMMs (" + f"{10 * rot_flop / rot_s / 1e12:.0f}" + " int8 TOP/s of 4500 nominal)"}
+        solve_roof = {"kernel": f"solve_warp_kernel<{p}> (per-SNP REML/ML Brent, FP64 CUDA cores)", "bound": "fp64-cuda-core",
+                      "achieved": solve_flop / solve_s / 1e12 if solve_s > 0 else 0.0, "peak": fp64_core_peak,
+                      "unit": "TFLOP/s", "frac": (solve_flop / solve_s / 1e12 / fp64_core_peak) if solve_s > 0 else None,
+                      "traffic": None, "launch_ms": st["solve"],
+                      "algorithmic_flop_per_launch": solve_flop,
+                      "peak_source": "2 x 18.0 T DFMA/s measured on this pool's B200 (tools/fp64_probe.cu); the algorithmic "
+                                     "count charges 1 flop per divide / log, which cost 9.5 / 51 DFMA-equivalents"}
+        dominant = solve_roof if st["solve"] >= st["rotate"] else rot_roof
         line = {
             "metric": "SNPs/sec exact -lmm scan (n=20k)", "value": value, "unit": "SNPs/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": config,
+            "data": "synthetic", "config": dict(config, rotation=("fp64-dmma" if args.rotate_variant == 0 else "int8-sliced-exact")),
             "e2e": {"value": e2e_value, "unit": "SNPs/s", "h2d_bytes_per_step": B * bps,
                     "d2h_bytes_per_step": kept_e2e // max(args.steps, 1) * (cols * 8 + 4) + B * (16 + 4) + 4,
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "rotate_dmma_kernel (FP64 DMMA eigen-rotation)", "bound": "tensor",
-                         "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": (achieved / fp64_peak) if fp64_peak > 0 else None, "traffic": None,
-                         "peak_source": "cuBLAS DGEMM (M=4096,N=K=n) measured in this run; MEASURED_PEAKS.json "
-                                        "holds no FP64 figure",
-                         "algorithmic_flop_per_launch": 2.0 * n * n * kept, "launch_ms": st["rotate"]},
+            "roofline": dominant, "roofline_rotation": rot_roof, "roofline_solve": solve_roof,
             "stage_ms_last_step": st,
-            "solve": {"mean_objective_evals_per_snp": mean_evals,
-                      "algorithmic_gflop_per_s": (solve_flop / (st["solve"] * 1e-3) / 1e9) if st["solve"] > 0 else None},
-            "decode": {"hbm_gb_per_s": ((B * bps + kept * n * 8) / (st["decode"] * 1e-3) / 1e9) if st["decode"] > 0 else None},
+            "solve": {"mean_objective_evals_per_snp": mean_evals},
+            "decode": {"hbm_gb_per_s": ((B * bps + kept * n * (8 if args.rotate_variant == 0 else 3)) / (st["decode"] * 1e-3) / 1e9) if st["decode"] > 0 else None},
             "null_model": {"lambda": lbd, "ml0": ml0, "reml0": reml0, "setup_s": setup_s},
             "kept_snps_per_step": kept, "clocks": clocks,
         }

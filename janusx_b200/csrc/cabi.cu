@@ -66,7 +66,23 @@ int upload_small(Model& m, const double* s, const double* xcov, const double* y)
     std::vector<double> xt(p * m.ldn, 0.0);
     for (size_t i = 0; i < n; ++i)
         for (size_t r = 0; r < p; ++r) xt[r * m.ldn + i] = xcov[i * p + r];
-    if (s) JXB_CUDA_OK(cudaMemcpyAsync(m.s, s, n * sizeof(double), cudaMemcpyHostToDevice, m.stream));
+    if (s) {
+        JXB_CUDA_OK(cudaMemcpyAsync(m.s, s, n * sizeof(double), cudaMemcpyHostToDevice, m.stream));
+        m.s_host.assign(s, s + n);
+    }
+    // interleaved K3 records; padding samples: s = 1 (so v > 0), everything else 0
+    std::vector<double> rec(m.ldn * m.rs, 0.0);
+    for (size_t i = 0; i < m.ldn; ++i) {
+        double* r = rec.data() + i * m.rs;
+        if (i < n) {
+            r[0] = m.s_host[i];
+            r[1] = y[i];
+            for (size_t c = 0; c < p; ++c) r[2 + c] = xcov[i * p + c];
+        } else {
+            r[0] = 1.0;
+        }
+    }
+    JXB_CUDA_OK(cudaMemcpyAsync(m.rec, rec.data(), rec.size() * sizeof(double), cudaMemcpyHostToDevice, m.stream));
     JXB_CUDA_OK(cudaMemcpyAsync(m.y, y, n * sizeof(double), cudaMemcpyHostToDevice, m.stream));
     JXB_CUDA_OK(cudaMemcpyAsync(m.xt, xt.data(), xt.size() * sizeof(double), cudaMemcpyHostToDevice, m.stream));
     JXB_CUDA_OK(cudaStreamSynchronize(m.stream));
@@ -122,6 +138,8 @@ int model_alloc(int device, size_t n, size_t p, bool with_ut, jxb_model** out) {
     rc |= dev_alloc(&m.s, n);
     rc |= dev_alloc(&m.y, n);
     rc |= dev_alloc(&m.xt, p * m.ldn);
+    m.rs = (p + 2 + 1) / 2 * 2;
+    rc |= dev_alloc(&m.rec, m.ldn * m.rs);
     rc |= dev_alloc(&m.n_kept, 8);
     rc |= dev_alloc(&h->scal, 16);
     rc |= dev_alloc(&m.fx_w, m.ldn);
@@ -142,6 +160,7 @@ int ensure_capacity(jxb_model* h, size_t rows, size_t bps, bool need_g) {
         const size_t cap = round_up(std::max<size_t>(rows, 256), kRotBM);
         int rc = 0;
         rc |= dev_alloc(&m.rot, cap * m.ldc);
+        if (!rc) cudaMemset(m.rot, 0, cap * m.ldc * sizeof(float));   // K3 reads the zero padding past n
         rc |= dev_alloc(&m.out, cap * 8);
         rc |= dev_alloc(&m.evals, cap);
         rc |= dev_alloc(&m.counts, cap * 4);
@@ -415,7 +434,7 @@ void jxb_model_destroy(jxb_model* h) {
     Model& m = h->m;
     cudaSetDevice(m.device);
     if (m.stream) cudaStreamSynchronize(m.stream);
-    void* ptrs[] = {m.s, m.y, m.xt, m.ut, m.g64, m.rot, m.rotT, m.out, m.evals, m.packed, m.counts, m.af, m.src_row,
+    void* ptrs[] = {m.s, m.y, m.xt, m.rec, m.ut, m.g64, m.rot, m.rotT, m.out, m.evals, m.packed, m.counts, m.af, m.src_row,
                     m.n_kept, m.sample_idx, m.stage_f32, m.fx_w, m.fx_py, m.fx_wx, m.fx_scal, h->missr, h->mask,
                     h->scal, m.q8, m.q8_inv_scale, m.q8_rk, m.a8, m.coef, m.flags8, m.c32, m.lt_ws};
     for (void* p : ptrs)

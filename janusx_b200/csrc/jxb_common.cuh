@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <vector>
 
 namespace jxb {
 
@@ -41,8 +42,11 @@ struct Model {
     double* s = nullptr;
     double* y = nullptr;
     double* xt = nullptr;
+    double* rec = nullptr;     // [round_up(n,32)][rs] interleaved per-sample records for K3 (s, y, x..)
+    size_t rs = 0;
     double* ut = nullptr;      // may be null for rotated-input-only use
     bool owns = true;
+    std::vector<double> s_host;  // host copy of S (records are rebuilt when Xcov / y change)
     // scan workspace (grown on demand)
     size_t cap_rows = 0;
     double* g64 = nullptr;     // [cap_rows_pad][ldk] decoded+centred genotypes (GEMM A operand)

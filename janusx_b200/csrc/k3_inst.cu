@@ -11,31 +11,34 @@
 
 namespace jxb {
 
+// warps per CTA: the staging buffers of 8 warps no longer fit 227 KB of shared memory from 6 covariates on
+constexpr int kWarps = (JXB_P <= 5) ? 8 : 4;
+
 int JXB_CAT(k3_launch_solve_p, JXB_P)(const k3::ModelView& mv, int blocks, const float* rot, size_t ldc,
                                       int max_rows, const int32_t* n_rows_dev, const SolveParams& sp, double* out,
                                       int out_cols, int32_t* evals, int32_t* queue, cudaStream_t st) {
-    constexpr int kSmem = 8 * 2 * k3::WarpDims<JXB_P, true>::SMEM_DOUBLES * (int)sizeof(double);
+    constexpr int kSmem = kWarps * JXB_K3_BUFS * k3::WarpDims<JXB_P, true>::SMEM_DOUBLES * (int)sizeof(double);
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(k3::solve_warp_kernel<JXB_P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
         attr = true;
     }
-    k3::solve_warp_kernel<JXB_P><<<blocks, 256, kSmem, st>>>(mv, rot, ldc, max_rows, n_rows_dev, sp, out, out_cols,
+    k3::solve_warp_kernel<JXB_P><<<blocks, kWarps * 32, kSmem, st>>>(mv, rot, ldc, max_rows, n_rows_dev, sp, out, out_cols,
                                                             evals, queue);
     return 0;
 }
 
 int JXB_CAT(k3_solve_blocks_per_sm_p, JXB_P)() {
-    constexpr int kSmem = 8 * 2 * k3::WarpDims<JXB_P, true>::SMEM_DOUBLES * (int)sizeof(double);
+    constexpr int kSmem = kWarps * JXB_K3_BUFS * k3::WarpDims<JXB_P, true>::SMEM_DOUBLES * (int)sizeof(double);
     int nb = 1;
     cudaFuncSetAttribute(k3::solve_warp_kernel<JXB_P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k3::solve_warp_kernel<JXB_P>, 256, kSmem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k3::solve_warp_kernel<JXB_P>, kWarps * 32, kSmem);
     return nb < 1 ? 1 : nb;
 }
 
 int JXB_CAT(k3_launch_null_p, JXB_P)(const k3::ModelView& mv, int kind, double low, double high, int max_iter,
                                      double tol, int has_init, double init, double* out_dev, cudaStream_t st) {
-    constexpr int kSmem = 2 * k3::WarpDims<JXB_P, false>::SMEM_DOUBLES * (int)sizeof(double);
+    constexpr int kSmem = JXB_K3_BUFS * k3::WarpDims<JXB_P, false>::SMEM_DOUBLES * (int)sizeof(double);
     k3::null_warp_kernel<JXB_P><<<1, 32, kSmem, st>>>(mv, kind, low, high, max_iter, tol, has_init, init, out_dev);
     return 0;
 }

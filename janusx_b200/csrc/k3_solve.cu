@@ -20,6 +20,7 @@ using namespace k3;
 ModelView view_of(const Model& m) {
     ModelView v;
     v.s = m.s; v.y = m.y; v.xt = m.xt; v.ldn = m.ldn; v.n = (int)m.n; v.p = (int)m.p;
+    v.rec = m.rec; v.rs = (int)m.rs;
     return v;
 }
 
@@ -72,7 +73,7 @@ int launch_solve(const Model& m, const float* rot, size_t ldc, size_t max_rows, 
 #undef B_DYN
     // persistent warps: fill every SM, never more warps than SNPs
     const int sms = sm_count(m.device);
-    int blocks = (int)std::min<size_t>((size_t)sms * per_sm, (max_rows + 7) / 8);
+    int blocks = (int)std::min<size_t>((size_t)sms * per_sm, (max_rows + 3) / 4);
     if (blocks < 1) blocks = 1;
 #define S_STATIC(P) \
     k3_launch_solve_p##P(mv, blocks, rot, ldc, (int)max_rows, n_rows_dev, sp, out, out_cols, evals, queue, st)

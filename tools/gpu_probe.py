@@ -48,7 +48,7 @@ def main():
         hi = (packed >> 1) & 0x55
         packed = (packed & ~(lo & ~hi)).contiguous()
         kw = dict(maf_thr=0.0, miss_thr=1.0, het_thr=1.0, mode="lmm2", low=-2.0, high=2.0, init=0.0, nullml=-1e4)
-        for variant in (0, 2, 1):
+        for variant in [int(v) for v in os.environ.get('PROBE_VARIANTS', '0,2,1').split(',')]:
             if variant == 1 and n > 6000:
                 continue
             lib.jxb_set_rotate_variant(variant)
