@@ -41,8 +41,9 @@ def parse_args():
     ap.add_argument("--grm-snps", type=int, default=int(os.environ.get("JXB_BENCH_GRM_SNPS", 50000)))
     ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("JXB_BENCH_CPU_SAMPLE", 1024)))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--rotate-variant", type=int, default=int(os.environ.get("JXB_BENCH_ROTATE", 2)),
-                    help="0 = FP64 DMMA GEMM, 2 = exact int8-sliced tensor-core rotation (default)")
+    ap.add_argument("--rotate-variant", type=int, default=int(os.environ.get("JXB_BENCH_ROTATE", 3)),
+                    help="3 = hand-written tcgen05 int8-sliced exact rotation (default), 2 = same via cuBLASLt, "
+                         "0 = FP64 DMMA GEMM")
     return ap.parse_args()
 
 
@@ -365,7 +366,8 @@ def main():
         solve_s = st["solve"] * 1e-3
         fp64_core_peak = 36.0      # TFLOP/s: 18.0 T DFMA/s measured with tools/fp64_probe.cu (profiles/r1_fp64_probe.txt)
         rot_roof = {"kernel": ("rotate_dmma_kernel (FP64 DMMA GEMM)" if args.rotate_variant == 0 else
-                               "int8-sliced exact rotation (10 slice GEMMs + recombine_kernel)"),
+                               ("i8_rotate_kernel (tcgen05 int8-sliced exact rotation, 2 passes)" if args.rotate_variant == 3 else
+                                "int8-sliced exact rotation (10 cuBLASLt slice GEMMs + recombine_kernel)")),
                     "bound": "tensor", "achieved": rot_flop / rot_s / 1e12 if rot_s > 0 else 0.0, "peak": fp64_peak,
                     "unit": "TFLOP/s (FP64-equivalent)", "frac": (rot_flop / rot_s / 1e12 / fp64_peak) if rot_s > 0 and fp64_peak > 0 else None,
                     "traffic": None, "launch_ms": st["rotate"],
@@ -384,7 +386,7 @@ def main():
             "metric": "SNPs/sec exact -lmm scan (n=20k)", "value": value, "unit": "SNPs/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": dict(config, rotation=("fp64-dmma" if args.rotate_variant == 0 else "int8-sliced-exact")),
+            "data": "synthetic", "config": dict(config, rotation={0: "fp64-dmma", 1: "fp64-cuda-core", 2: "int8-sliced-exact (cuBLASLt)", 3: "int8-sliced-exact (tcgen05)"}[args.rotate_variant]),
             "e2e": {"value": e2e_value, "unit": "SNPs/s", "h2d_bytes_per_step": B * bps,
                     "d2h_bytes_per_step": kept_e2e // max(args.steps, 1) * (cols * 8 + 4) + B * (16 + 4) + 4,
                     "ms_per_step": e2e_ms / args.steps},

@@ -27,7 +27,10 @@ namespace jxb {
 static thread_local std::string g_err;
 static std::atomic<uint64_t> g_launches{0};
 static int g_timing = 0;
-static int g_rotate_variant = 0;
+// rotation for packed additive scans: 3 = hand-written tcgen05 int8-sliced exact rotation (default),
+// 2 = same arithmetic with cuBLASLt slice GEMMs, 0 = FP64 DMMA GEMM, 1 = CUDA-core cross-check.
+// Chunk entry points that take arbitrary f32 genotypes always use the FP64 DMMA GEMM (or 1).
+static int g_rotate_variant = 3;
 
 void set_error(const std::string& msg) { g_err = msg; }
 int fail(int code, const std::string& msg) {
@@ -330,7 +333,7 @@ int scan_device_stages(jxb_model* h, const uint8_t* packed_dev, size_t bps, size
     note_launch(1);
     if (rc) return rc;
     tick(h, 2);
-    if (g_rotate_variant == 2 && qc->genetic_model == JXB_MODEL_ADD) {
+    if ((g_rotate_variant == 2 || g_rotate_variant == 3) && qc->genetic_model == JXB_MODEL_ADD) {
         // int8-sliced exact rotation (k2_int8.cu): int8 operands instead of the f64 block (additive coding
         // only: for dom/rec/het the T_2 coefficient is O(1) and the DMMA path is used)
         rc = prepare_int8_slices(m, m.stream);
@@ -345,7 +348,8 @@ int scan_device_stages(jxb_model* h, const uint8_t* packed_dev, size_t bps, size
         JXB_CUDA_OK(cudaMemcpyAsync(&nk, m.n_kept, sizeof nk, cudaMemcpyDeviceToHost, m.stream));
         JXB_CUDA_OK(cudaMemcpyAsync(&anym, m.flags8, sizeof anym, cudaMemcpyDeviceToHost, m.stream));
         JXB_CUDA_OK(cudaStreamSynchronize(m.stream));
-        rc = launch_rotate_int8_lib(m, (size_t)nk, anym != 0, m.stream);
+        rc = g_rotate_variant == 3 ? launch_rotate_int8_tc(m, (size_t)nk, anym != 0, m.stream)
+                                   : launch_rotate_int8_lib(m, (size_t)nk, anym != 0, m.stream);
         if (rc) return rc;
     } else {
         rc = launch_decode_center(packed_dev, bps, m.src_row, m.n_kept, rows, n_full, sidx_dev, m.n, m.af, m.counts,
@@ -353,7 +357,7 @@ int scan_device_stages(jxb_model* h, const uint8_t* packed_dev, size_t bps, size
         note_launch(1);
         if (rc) return rc;
         tick(h, 3);
-        rc = launch_rotate(m, rows, m.n_kept, m.rot, m.ldc, 0, m.stream, g_rotate_variant == 2 ? 0 : g_rotate_variant);
+        rc = launch_rotate(m, rows, m.n_kept, m.rot, m.ldc, 0, m.stream, g_rotate_variant >= 2 ? 0 : g_rotate_variant);
         note_launch(1);
         if (rc) return rc;
     }
@@ -436,12 +440,14 @@ void jxb_model_destroy(jxb_model* h) {
     if (m.stream) cudaStreamSynchronize(m.stream);
     void* ptrs[] = {m.s, m.y, m.xt, m.rec, m.ut, m.g64, m.rot, m.rotT, m.out, m.evals, m.packed, m.counts, m.af, m.src_row,
                     m.n_kept, m.sample_idx, m.stage_f32, m.fx_w, m.fx_py, m.fx_wx, m.fx_scal, h->missr, h->mask,
-                    h->scal, m.q8, m.q8_inv_scale, m.q8_rk, m.a8, m.coef, m.flags8, m.c32, m.lt_ws};
+                    h->scal, m.q8, m.q8_inv_scale, m.q8_rk, m.a8, m.coef, m.flags8, m.c32, m.lt_ws, m.corr64};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->timing_ready)
         for (auto& e : h->ev) cudaEventDestroy(e);
     if (m.stream) cudaStreamDestroy(m.stream);
+    for (void* t : {m.tmap_a8, m.tmap_q8_7, m.tmap_q8_3})
+        if (t) free(t);
     if (m.tmap_ut) free(m.tmap_ut);
     if (m.tmap_g) free(m.tmap_g);
     delete h;

@@ -75,6 +75,8 @@ struct Model {
     int32_t* flags8 = nullptr;                           // [0] = any missing call in the batch
     int32_t* c32 = nullptr; size_t c32_elems = 0;        // int32 slice results (library variant)
     void* lt_ws = nullptr; size_t lt_ws_bytes = 0;
+    double* corr64 = nullptr; size_t corr_rows = 0, ld_corr = 0;   // f64 correction terms (tcgen05 variant)
+    void* tmap_a8 = nullptr; size_t tmap_a8_rows = 0; void* tmap_q8_7 = nullptr; void* tmap_q8_3 = nullptr;
     // fixed-lambda cache (A14)
     float* fx_w = nullptr; float* fx_py = nullptr; float* fx_wx = nullptr; double* fx_scal = nullptr;
     double fx_log10_lbd = 0.0; bool fx_valid = false;
@@ -124,5 +126,6 @@ int launch_decode_int8(Model& m, const uint8_t* packed, size_t bps, const int32_
                        size_t max_rows, size_t n_full, const int64_t* sample_idx, const float* af_by_src,
                        const int32_t* counts_by_src, int model_code, cudaStream_t st);
 int launch_rotate_int8_lib(Model& m, size_t rows, bool has_missing, cudaStream_t st);
+int launch_rotate_int8_tc(Model& m, size_t rows, bool has_missing, cudaStream_t st);   // k2_i8mma.cu
 
 }  // namespace jxb

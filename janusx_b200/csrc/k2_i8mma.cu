@@ -1,0 +1,369 @@
+// k2_i8mma.cu -- hand-written tcgen05 (sm_100a) kernel for the int8-sliced exact rotation (see k2_int8.cu for
+// the arithmetic): all digit planes of a U^T column block are stacked into ONE MMA N dimension so a 128-row
+// genotype tile meets every slice in a single tcgen05.mma, the int32 accumulators live in TMEM, and the
+// epilogue recombines the slices by Horner in f64 straight out of TMEM -- the int32 slice results never
+// touch HBM.
+//
+// Tiling (pass D, 7 slices): CTA tile = 256 genotype rows (two M=128 sub-tiles) x 32 eigen-directions;
+//   B tile  = [7 slices][32 rows][128 B of K]  -> MMA N = 224, one TMA box from the 3-D plane tensor
+//   A tiles = 2 x [128 rows][128 B of K]       -> two TMA boxes
+//   TMEM    = 2 accumulators x 224 columns (int32) of the 512-column allocation
+//   k-slab  = 128 bytes (SWIZZLE_128B), 4 tcgen05.mma.kind::i8 (K = 32) per sub-tile per slab, 3 stages (180 KB)
+// Pass 2 (top 3 slices, hom indicator) uses 64 eigen-directions per tile (N = 192); pass M (missing indicator)
+// is pass D's shape.  Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2..5 = epilogue (tcgen05.ld 32x32b, one TMEM lane quarter each).  Persistent CTAs, grouped raster.
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstdlib>
+
+#include "jxb_common.cuh"
+
+namespace jxb {
+
+namespace {
+
+constexpr int TM = 128;
+constexpr int MSUB = 2;
+constexpr int KSLAB = 128;                       // bytes of K per stage row
+constexpr int STAGES = 3;
+constexpr int A_STAGE = MSUB * TM * KSLAB;       // 32 KB
+constexpr int NTHREADS = 192;
+constexpr int GROUP_M = 16;
+constexpr int ACC_COLS = 256;                    // TMEM column stride between the two accumulators
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] x B[smem desc], int8 x int8 -> int32
+__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, int32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major SWIZZLE_128B operand: 128-byte rows, 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFFu);
+    d |= (uint64_t)1 << 16;                 // leading byte offset (unused for swizzled K-major) = 1
+    d |= (uint64_t)(1024 >> 4) << 32;       // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+    return d;
+}
+// cute::UMMA::InstrDescriptor: S32 accumulate, int8 x int8, both K-major
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void tile_coords(int tile, int mt_count, int nt_count, int& mt, int& nt) {
+    const int per_group = GROUP_M * nt_count;
+    const int group = tile / per_group;
+    const int first_m = group * GROUP_M;
+    const int gsize = min(GROUP_M, mt_count - first_m);
+    const int in_group = tile - group * per_group;
+    mt = first_m + in_group % gsize;
+    nt = in_group / gsize;
+}
+
+// mode 0: corr  = coef[2] * T * is        (top slices of the hom indicator; T carries the 256^slice0 factor)
+// mode 1: corr += coef[3] * T * is        (missing indicator)
+// mode 2: rot   = f32(coef[0] * rk + coef[1] * T * is + corr)
+template <int NSL, int CG>
+__global__ void __launch_bounds__(NTHREADS, 1)
+i8_rotate_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, int a_plane,
+                 int slice0, int mode, int rows, int n, int kslabs, const double* __restrict__ coef,
+                 const double* __restrict__ inv_scale, const double* __restrict__ rk, double* __restrict__ corr,
+                 size_t ld_corr, float* __restrict__ rot, size_t ldc) {
+    constexpr int NB = NSL * CG;                    // MMA N
+    constexpr int B_STAGE = NB * KSLAB;
+    constexpr int STAGE = A_STAGE + B_STAGE;
+    static_assert(NB % 16 == 0 && NB <= 256, "invalid MMA N");
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t tiles_s = (raw + 1023u) & ~1023u;
+    const uint32_t bars = tiles_s + STAGES * STAGE;     // full[S], empty[S], tmem_full, tmem_empty
+    const uint32_t bar_tfull = bars + 8 * (2 * STAGES);
+    const uint32_t bar_tempty = bars + 8 * (2 * STAGES + 1);
+    const uint32_t tmem_slot = bars + 8 * (2 * STAGES + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    const int mt_count = (rows + MSUB * TM - 1) / (MSUB * TM);
+    const int nt_count = (n + CG - 1) / CG;
+    const int n_tiles = mt_count * nt_count;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bars + 8 * s, 1);
+            mbar_init(bars + 8 * (STAGES + s), 1);       // released by tcgen05.commit
+        }
+        mbar_init(bar_tfull, 1);
+        mbar_init(bar_tempty, 4);                        // one arrive per epilogue warp
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                int mt, nt;
+                tile_coords(tile, mt_count, nt_count, mt, nt);
+                for (int kb = 0; kb < kslabs; ++kb) {
+                    mbar_wait(bars + 8 * (STAGES + stage), phase ^ 1u);
+                    const uint32_t full = bars + 8 * stage;
+                    mbar_expect_tx(full, STAGE);
+                    const uint32_t sa = tiles_s + stage * STAGE;
+                    tma_load_3d(sa, &tm_a, kb * KSLAB, mt * MSUB * TM, a_plane, full);
+                    tma_load_3d(sa + TM * KSLAB, &tm_a, kb * KSLAB, mt * MSUB * TM + TM, a_plane, full);
+                    tma_load_3d(sa + A_STAGE, &tm_b, kb * KSLAB, nt * CG, slice0, full);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(TM, NB);
+            int stage = 0;
+            uint32_t phase = 0, tphase = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                mbar_wait(bar_tempty, tphase ^ 1u);          // epilogue has drained the accumulators
+                tc_fence_after();
+                for (int kb = 0; kb < kslabs; ++kb) {
+                    mbar_wait(bars + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t sa = tiles_s + stage * STAGE;
+                    const uint64_t db = make_desc(sa + A_STAGE);
+#pragma unroll
+                    for (int sub = 0; sub < MSUB; ++sub) {
+                        const uint64_t da = make_desc(sa + sub * TM * KSLAB);
+#pragma unroll
+                        for (int s = 0; s < KSLAB / 32; ++s)
+                            tc_mma_i8(tmem_base + sub * ACC_COLS, da + 2 * s, db + 2 * s, idesc, (kb | s) ? 1u : 0u);
+                    }
+                    tc_commit(bars + 8 * (STAGES + stage));   // frees the smem stage when these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+                tc_commit(bar_tfull);                          // accumulators complete
+                tphase ^= 1u;
+            }
+        }
+    } else {
+        // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+        const int quarter = warp & 3;
+        uint32_t tphase = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            int mt, nt;
+            tile_coords(tile, mt_count, nt_count, mt, nt);
+            mbar_wait(bar_tfull, tphase);
+            tc_fence_after();
+            const int k0 = nt * CG;
+#pragma unroll
+            for (int sub = 0; sub < MSUB; ++sub) {
+                const int r = mt * MSUB * TM + sub * TM + quarter * 32 + lane;
+                const bool live = r < rows;
+                double c_a = 0.0, c_t = 0.0;
+                if (live) {
+                    const double* cf = coef + 4 * (size_t)r;
+                    c_a = cf[0];
+                    c_t = mode == 0 ? cf[2] : (mode == 1 ? cf[3] : cf[1]);
+                }
+                const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + sub * ACC_COLS;
+#pragma unroll
+                for (int cb = 0; cb < CG / 8; ++cb) {
+                    int32_t v[NSL][8];
+#pragma unroll
+                    for (int l = 0; l < NSL; ++l) tc_ld8(tbase + l * CG + cb * 8, v[l]);
+                    tc_wait_ld();
+                    const int kc = k0 + cb * 8;
+                    if (live && kc < n) {
+                        double o[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            double t = 0.0;
+#pragma unroll
+                            for (int l = NSL - 1; l >= 0; --l) t = t * 256.0 + (double)v[l][j];
+                            const int k = min(kc + j, n - 1);
+                            t *= inv_scale[k];
+                            if (mode == 0) {
+                                o[j] = c_t * (t * 4294967296.0);              // slice0 = 4: 256^4
+                            } else if (mode == 1) {
+                                o[j] = corr[(size_t)r * ld_corr + k] + c_t * t;
+                            } else {
+                                o[j] = c_a * rk[k] + c_t * t + corr[(size_t)r * ld_corr + k];
+                            }
+                        }
+                        if (mode == 2) {
+                            float* dst = rot + (size_t)r * ldc + kc;
+                            if (kc + 8 <= n) {
+                                reinterpret_cast<float4*>(dst)[0] = make_float4((float)o[0], (float)o[1], (float)o[2], (float)o[3]);
+                                reinterpret_cast<float4*>(dst)[1] = make_float4((float)o[4], (float)o[5], (float)o[6], (float)o[7]);
+                            } else {
+                                for (int j = 0; j < 8 && kc + j < n; ++j) dst[j] = (float)o[j];
+                            }
+                        } else {
+                            double* dst = corr + (size_t)r * ld_corr + kc;
+                            if (kc + 8 <= n) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) reinterpret_cast<double2*>(dst)[j] = make_double2(o[2 * j], o[2 * j + 1]);
+                            } else {
+                                for (int j = 0; j < 8 && kc + j < n; ++j) dst[j] = o[j];
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty);
+            tphase ^= 1u;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// 3-D byte tensor [planes][rows][ld8] with a {128 B, box_rows, box_planes} box, SWIZZLE_128B
+int encode_planes(CUtensorMap* tm, void* base, size_t ld8, size_t rows, size_t planes, int box_rows, int box_planes) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return fail(-101, "cuTensorMapEncodeTiled is unavailable from the CUDA driver");
+    cuuint64_t dims[3] = {(cuuint64_t)ld8, (cuuint64_t)rows, (cuuint64_t)planes};
+    cuuint64_t strides[2] = {(cuuint64_t)ld8, (cuuint64_t)ld8 * rows};
+    cuuint32_t box[3] = {(cuuint32_t)KSLAB, (cuuint32_t)box_rows, (cuuint32_t)box_planes};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(-102, "cuTensorMapEncodeTiled(int8 planes) failed with code " + std::to_string((int)r));
+    return 0;
+}
+
+template <int NSL, int CG>
+int launch_pass(Model& m, const CUtensorMap& tm_a, const CUtensorMap& tm_b, int a_plane, int slice0, int mode,
+                size_t rows, cudaStream_t st) {
+    constexpr int STAGE = A_STAGE + NSL * CG * KSLAB;
+    constexpr int SMEM = STAGES * STAGE + 1024 + 256;
+    static bool attr = false;
+    if (!attr) {
+        JXB_CUDA_OK(cudaFuncSetAttribute(i8_rotate_kernel<NSL, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        attr = true;
+    }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m.device);
+    const size_t tiles = ((rows + MSUB * TM - 1) / (MSUB * TM)) * ((m.n + CG - 1) / CG);
+    const int grid = (int)std::min<size_t>((size_t)sms, tiles);
+    i8_rotate_kernel<NSL, CG><<<grid, NTHREADS, SMEM, st>>>(tm_a, tm_b, a_plane, slice0, mode, (int)rows, (int)m.n,
+                                                           (int)(m.ld8 / KSLAB), m.coef, m.q8_inv_scale, m.q8_rk,
+                                                           m.corr64, m.ld_corr, m.rot, m.ldc);
+    note_launch(1);
+    JXB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+// Hand-written tcgen05 path: pass 2 (hom indicator, top 3 slices) -> [pass M (missing indicator)] -> pass D.
+int launch_rotate_int8_tc(Model& m, size_t rows, bool has_missing, cudaStream_t st) {
+    if (rows == 0) return 0;
+    const size_t ld_corr = round_up(m.n, 32);
+    if (!m.corr64 || m.corr_rows < m.a8_rows || m.ld_corr != ld_corr) {
+        if (m.corr64) cudaFree(m.corr64);
+        m.corr64 = nullptr;
+        JXB_CUDA_OK(cudaMalloc((void**)&m.corr64, m.a8_rows * ld_corr * sizeof(double)));
+        m.corr_rows = m.a8_rows;
+        m.ld_corr = ld_corr;
+    }
+    if (!m.tmap_a8 || m.tmap_a8_rows != m.a8_rows) {
+        if (!m.tmap_a8) m.tmap_a8 = aligned_alloc(64, sizeof(CUtensorMap));
+        int rc = encode_planes((CUtensorMap*)m.tmap_a8, m.a8, m.ld8, m.a8_rows, 3, TM, 1);
+        if (rc) return rc;
+        m.tmap_a8_rows = m.a8_rows;
+    }
+    if (!m.tmap_q8_7) {
+        m.tmap_q8_7 = aligned_alloc(64, sizeof(CUtensorMap));
+        m.tmap_q8_3 = aligned_alloc(64, sizeof(CUtensorMap));
+        int rc = encode_planes((CUtensorMap*)m.tmap_q8_7, m.q8, m.ld8, m.q8_rows, 7, 32, 7);
+        if (!rc) rc = encode_planes((CUtensorMap*)m.tmap_q8_3, m.q8, m.ld8, m.q8_rows, 7, 64, 3);
+        if (rc) return rc;
+    }
+    const CUtensorMap& ta = *(const CUtensorMap*)m.tmap_a8;
+    int rc = launch_pass<3, 64>(m, ta, *(const CUtensorMap*)m.tmap_q8_3, /*a_plane=*/1, /*slice0=*/4, /*mode=*/0, rows, st);
+    if (!rc && has_missing)
+        rc = launch_pass<7, 32>(m, ta, *(const CUtensorMap*)m.tmap_q8_7, /*a_plane=*/2, 0, /*mode=*/1, rows, st);
+    if (!rc) rc = launch_pass<7, 32>(m, ta, *(const CUtensorMap*)m.tmap_q8_7, /*a_plane=*/0, 0, /*mode=*/2, rows, st);
+    return rc;
+}
+
+}  // namespace jxb

@@ -377,8 +377,9 @@ def _get_model(s, xcov, y_rot, u_t=None) -> DeviceModel:
 
 
 def set_rotate_variant(variant: int) -> None:
-    """Rotation kernel used by the packed scans: 0 = FP64 DMMA/TMA GEMM (default), 1 = CUDA-core cross-check,
-    2 = exact int8-sliced tensor-core rotation (additive coding; see csrc/k2_int8.cu)."""
+    """Rotation kernel used by the packed scans (default 3): 0 = FP64 DMMA/TMA GEMM, 1 = CUDA-core cross-check,
+    2 = exact int8-sliced tensor-core rotation, slice GEMMs through cuBLASLt (additive coding; csrc/k2_int8.cu),
+    3 = the same arithmetic on the hand-written tcgen05/TMEM kernel (csrc/k2_i8mma.cu)."""
     lib().jxb_set_rotate_variant(int(variant))
 
 

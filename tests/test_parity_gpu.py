@@ -343,6 +343,12 @@ def test_int8_sliced_rotation_variant(jx, oracle):
             mdl = jx.DeviceModel(case.s, nm["xcov"], nm["y"], nm["ut"])
             jx.set_rotate_variant(2)
             k2, af2, ms2, out2 = mdl.scan_packed(case.packed, n, low=nm["low"], high=nm["high"])
+            # variant 3: the hand-written tcgen05 kernel computes exactly what the library slice GEMMs compute
+            jx.set_rotate_variant(3)
+            k3, af3, ms3, out3 = mdl.scan_packed(case.packed, n, low=nm["low"], high=nm["high"])
+            assert np.array_equal(k3, keep)
+            assert_results_close(out3, want)
+            assert_results_close(out3, out2)
             jx.set_rotate_variant(0)
             k0, af0, ms0, out0 = mdl.scan_packed(case.packed, n, low=nm["low"], high=nm["high"])
             assert np.array_equal(k2, keep) and np.array_equal(ms2, missing)
@@ -358,4 +364,4 @@ def test_int8_sliced_rotation_variant(jx, oracle):
             d0 = mdl.scan_packed(case.packed, n, low=nm["low"], high=nm["high"], genetic_model="dom")[3]
             assert np.array_equal(d2, d0, equal_nan=True)
     finally:
-        jx.set_rotate_variant(0)
+        jx.set_rotate_variant(3)

@@ -48,7 +48,7 @@ def main():
         hi = (packed >> 1) & 0x55
         packed = (packed & ~(lo & ~hi)).contiguous()
         kw = dict(maf_thr=0.0, miss_thr=1.0, het_thr=1.0, mode="lmm2", low=-2.0, high=2.0, init=0.0, nullml=-1e4)
-        for variant in [int(v) for v in os.environ.get('PROBE_VARIANTS', '0,2,1').split(',')]:
+        for variant in [int(v) for v in os.environ.get('PROBE_VARIANTS', '0,3,2,1').split(',')]:
             if variant == 1 and n > 6000:
                 continue
             lib.jxb_set_rotate_variant(variant)
@@ -62,7 +62,7 @@ def main():
                                         "rotate_tflops": 2.0 * n * n * kept / (st["rotate"] * 1e-3) / 1e12,
                                         "snps_per_s": kept / (sum(st[k] for k in ("count_qc", "decode", "rotate", "solve")) * 1e-3),
                                         "mean_evals": float(ev.mean())}
-        lib.jxb_set_rotate_variant(0)
+        lib.jxb_set_rotate_variant(3)
         # rotation correctness at this size against torch f64 (first 256 rows)
         g = torch.randn((256, n), dtype=torch.float32, device="cuda")
         want = (g.double() @ ut.double().T).float().cpu().numpy()
