@@ -32,11 +32,12 @@ SEED = 20260609  # the reference's benchmark seed (scripts/benchmark.sh:36)
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=int(os.environ.get("JXB_BENCH_N", 20000)))
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("JXB_BENCH_BATCH", 16384)))
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("JXB_BENCH_BATCH", 56832)),
+                    help="SNPs per step; 56832 = 148 SMs x 12 warps x 32 SNPs = one full wave of the thread-per-SNP solve")
     ap.add_argument("--model", default=os.environ.get("JXB_BENCH_MODEL", "lmm2"), choices=["lmm", "lmm2", "fvlmm"])
     ap.add_argument("--grm-snps", type=int, default=int(os.environ.get("JXB_BENCH_GRM_SNPS", 50000)))
     ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("JXB_BENCH_CPU_SAMPLE", 1024)))
@@ -374,7 +375,7 @@ def main():
                     "peak_source": "cuBLAS DGEMM (M=4096,N=K=n) measured in this run; MEASURED_PEAKS.json holds no FP64 "
                                    "figure. frac > 1 for the int8-sliced variant: same f64-accurate result from 10 exact "
                                    "int8 slice GEMMs (" + f"{10 * rot_flop / rot_s / 1e12:.0f}" + " int8 TOP/s of 4500 nominal)"}
-        solve_roof = {"kernel": f"solve_warp_kernel<{p}> (per-SNP REML/ML Brent, FP64 CUDA cores)", "bound": "fp64-cuda-core",
+        solve_roof = {"kernel": (f"solve_thread_kernel<{p}>" if (args.rotate_variant == 3 and kept >= 32768) else f"solve_warp_kernel<{p}>") + " (per-SNP REML/ML Brent, FP64 CUDA cores)", "bound": "fp64-cuda-core",
                       "achieved": solve_flop / solve_s / 1e12 if solve_s > 0 else 0.0, "peak": fp64_core_peak,
                       "unit": "TFLOP/s", "frac": (solve_flop / solve_s / 1e12 / fp64_core_peak) if solve_s > 0 else None,
                       "traffic": None, "launch_ms": st["solve"],

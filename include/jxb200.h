@@ -141,8 +141,13 @@ void jxb_set_timing(int on);
 int jxb_last_stage_ms(jxb_model* m, float ms6[6]);
 /* raw stream handle (cudaStream_t) the model launches on, for callers timing with CUDA events */
 void* jxb_model_stream(jxb_model* m);
-/* choose the rotation kernel for subsequent scans: 0 = DMMA/TMA (default), 1 = CUDA-core cross-check */
+/* rotation kernel for subsequent packed additive scans: 3 = hand-written tcgen05 int8-sliced exact rotation
+ * (default), 2 = same arithmetic with cuBLASLt slice GEMMs, 0 = FP64 DMMA/TMA GEMM, 1 = CUDA-core cross-check.
+ * Chunk entry points taking arbitrary f32 genotypes always use the FP64 GEMM. */
 void jxb_set_rotate_variant(int variant);
+/* batches with at least this many kept SNPs use the one-thread-per-SNP solve kernel (default 32768);
+ * smaller ones the warp-per-SNP kernel.  Both reproduce the reference summation order. */
+void jxb_set_thread_solve_min_rows(size_t rows);
 
 /* ---- file level ------------------------------------------------------------------------------------
  * lmm_reml_assoc_bed_to_tsv_f32 / lmm_reml_lmm2_assoc_bed_to_tsv_f32 / fvlmm_assoc_bed_to_tsv_f32 --

@@ -19,6 +19,7 @@ struct jxb_model {
     uint8_t* mask = nullptr;      // [cap_rows] device (pre-keep mask)
     double* scal = nullptr;       // small device scratch (null fit outputs)
     size_t last_rows = 0;
+    bool rot_dirty = false;       // rot holds a transposed block: re-zero before the row-major kernels read padding
     int last_out_cols = 0;
 };
 
@@ -31,6 +32,7 @@ static int g_timing = 0;
 // 2 = same arithmetic with cuBLASLt slice GEMMs, 0 = FP64 DMMA GEMM, 1 = CUDA-core cross-check.
 // Chunk entry points that take arbitrary f32 genotypes always use the FP64 DMMA GEMM (or 1).
 static int g_rotate_variant = 3;
+static size_t g_thread_solve_min_rows = 32768;   // batches at least this large use the thread-per-SNP solve
 
 void set_error(const std::string& msg) { g_err = msg; }
 int fail(int code, const std::string& msg) {
@@ -195,6 +197,16 @@ int ensure_capacity(jxb_model* h, size_t rows, size_t bps, bool need_g) {
     return 0;
 }
 
+// rot may hold a transposed (SNP-minor) block from the large-batch path: restore the zero padding the
+// row-major kernels rely on before anything row-major is written or read
+int clean_rot(jxb_model* h) {
+    if (h->rot_dirty && h->m.rot) {
+        JXB_CUDA_OK(cudaMemsetAsync(h->m.rot, 0, h->m.cap_rows * h->m.ldc * sizeof(float), h->m.stream));
+        h->rot_dirty = false;
+    }
+    return 0;
+}
+
 int ensure_stage_f32(Model& m, size_t count) {
     if (count > m.stage_f32_cap) {
         JXB_CUDA_OK(cudaStreamSynchronize(m.stream));
@@ -290,6 +302,8 @@ int chunk_common(jxb_model* h, const float* host, size_t rows, bool rotated, con
     if (!rotated && !m.ut) return fail(-3, "u_t must be (n, n) and row-major U^T");
     rc = ensure_capacity(h, rows, 0, !rotated);
     if (rc) return rc;
+    rc = clean_rot(h);
+    if (rc) return rc;
     const size_t n = m.n;
     if (rotated) {
         JXB_CUDA_OK(cudaMemcpy2DAsync(m.rot, m.ldc * sizeof(float), host, n * sizeof(float), n * sizeof(float), rows,
@@ -319,7 +333,8 @@ int scan_device_stages(jxb_model* h, const uint8_t* packed_dev, size_t bps, size
                        const int64_t* sidx_dev, size_t n_sel, bool have_mask, const jxb_qc_cfg* qc,
                        const jxb_solve_cfg* cfg, int mode) {
     Model& m = h->m;
-    int rc;
+    int rc = clean_rot(h);
+    if (rc) return rc;
     tick(h, 1);
     rc = launch_count_qc(m, packed_dev, bps, rows, n_full, sidx_dev, n_sel, qc->maf_thr, qc->miss_thr, qc->het_thr,
                          m.counts, m.af, h->missr, m.stream);
@@ -348,10 +363,37 @@ int scan_device_stages(jxb_model* h, const uint8_t* packed_dev, size_t bps, size
         JXB_CUDA_OK(cudaMemcpyAsync(&nk, m.n_kept, sizeof nk, cudaMemcpyDeviceToHost, m.stream));
         JXB_CUDA_OK(cudaMemcpyAsync(&anym, m.flags8, sizeof anym, cudaMemcpyDeviceToHost, m.stream));
         JXB_CUDA_OK(cudaStreamSynchronize(m.stream));
-        rc = g_rotate_variant == 3 ? launch_rotate_int8_tc(m, (size_t)nk, anym != 0, m.stream)
+        // large batches: SNP-minor output + one-thread-per-SNP solve (no shared-memory transposition)
+        const bool thread_solve = g_rotate_variant == 3 && mode != 2 && m.p <= 8 && (size_t)nk >= g_thread_solve_min_rows;
+        if (thread_solve) {
+            // SNP-minor view rotT[round_up(n,32)][cap_rows]: the sample rows past n must read as zeros
+            const size_t n32 = round_up(m.n, 32);
+            if (n32 > m.n)
+                JXB_CUDA_OK(cudaMemsetAsync(m.rot + m.n * m.cap_rows, 0, (n32 - m.n) * m.cap_rows * sizeof(float), m.stream));
+        }
+        rc = g_rotate_variant == 3 ? launch_rotate_int8_tc(m, (size_t)nk, anym != 0, thread_solve, m.stream)
                                    : launch_rotate_int8_lib(m, (size_t)nk, anym != 0, m.stream);
         if (rc) return rc;
+        tick(h, 4);
+        if (thread_solve) {
+            const int oc = out_cols_of(cfg, mode);
+            h->last_out_cols = oc;
+            rc = launch_solve_thread(m, m.rot, m.cap_rows, (size_t)nk, nullptr, to_params(cfg, mode), m.out, oc, m.evals,
+                                     m.stream);
+            note_launch(1);
+        } else {
+            rc = run_solve(h, rows, m.n_kept, cfg, mode);
+        }
+        if (rc) return rc;
+        tick(h, 5);
+        h->last_rows = rows;
+        // the transposed epilogue may have written beyond column n of the row-major view: restore the zero
+        // padding the warp kernel relies on the next time it runs
+        if (thread_solve) h->rot_dirty = true;
+        return 0;
     } else {
+        rc = ensure_capacity(h, rows, 0, true);   // the FP64 path needs the f64 operand block
+        if (rc) return rc;
         rc = launch_decode_center(packed_dev, bps, m.src_row, m.n_kept, rows, n_full, sidx_dev, m.n, m.af, m.counts,
                                   qc->genetic_model, m.g64, m.ldk, nullptr, 0, m.stream);
         note_launch(1);
@@ -401,6 +443,7 @@ uint64_t jxb_launch_count(void) { return g_launches.load(); }
 
 void jxb_set_timing(int on) { g_timing = on; }
 void jxb_set_rotate_variant(int variant) { g_rotate_variant = variant; }
+void jxb_set_thread_solve_min_rows(size_t rows) { g_thread_solve_min_rows = rows; }
 
 int jxb_model_create(int device, size_t n, size_t p, const double* s, const double* xcov, const double* y,
                      const float* u_t, jxb_model** out) {
@@ -562,6 +605,8 @@ int jxb_rotate_block_f32(jxb_model* h, const float* snp, size_t rows, float* rot
     if (rows == 0) return 0;
     int rc = ensure_capacity(h, rows, 0, true);
     if (rc) return rc;
+    rc = clean_rot(h);
+    if (rc) return rc;
     const size_t n = m.n;
     rc = ensure_stage_f32(m, rows * n);
     if (rc) return rc;
@@ -585,7 +630,7 @@ int jxb_scan_packed_dev(jxb_model* h, const uint8_t* packed_dev, size_t bps, siz
     rc = check_cfg(cfg, mode);
     if (rc) return rc;
     if (rows == 0) { h->last_rows = 0; return 0; }
-    rc = ensure_capacity(h, rows, 0, true);
+    rc = ensure_capacity(h, rows, 0, false);
     if (rc) return rc;
     return scan_device_stages(h, packed_dev, bps, rows, n_full, sidx_dev, h->m.n, false, qc, cfg, mode);
 }
@@ -644,7 +689,7 @@ int jxb_scan_packed(jxb_model* h, const uint8_t* packed, size_t bps, size_t rows
     if (rows == 0) { if (n_kept_host) *n_kept_host = 0; return 0; }
     if (!packed) return fail(-2, "packed is null");
     Model& m = h->m;
-    rc = ensure_capacity(h, rows, bps, true);
+    rc = ensure_capacity(h, rows, bps, false);
     if (rc) return rc;
     tick(h, 0);
     JXB_CUDA_OK(cudaMemcpyAsync(m.packed, packed, rows * bps, cudaMemcpyHostToDevice, m.stream));

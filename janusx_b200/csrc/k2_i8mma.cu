@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 i8_rotate_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, int a_plane,
                  int slice0, int mode, int rows, int n, int kslabs, const double* __restrict__ coef,
                  const double* __restrict__ inv_scale, const double* __restrict__ rk, double* __restrict__ corr,
-                 size_t ld_corr, float* __restrict__ rot, size_t ldc) {
+                 size_t ld_corr, float* __restrict__ rot, size_t ldc, int transposed) {
     constexpr int NB = NSL * CG;                    // MMA N
     constexpr int B_STAGE = NB * KSLAB;
     constexpr int STAGE = A_STAGE + B_STAGE;
@@ -246,7 +246,12 @@ i8_rotate_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                                 o[j] = c_a * rk[k] + c_t * t + corr[(size_t)r * ld_corr + k];
                             }
                         }
-                        if (mode == 2) {
+                        if (mode == 2 && transposed) {
+                            // SNP-minor output for the thread-per-SNP solve: rotT[k][r], lanes = consecutive r
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                if (kc + j < n) rot[(size_t)(kc + j) * ldc + r] = (float)o[j];
+                        } else if (mode == 2) {
                             float* dst = rot + (size_t)r * ldc + kc;
                             if (kc + 8 <= n) {
                                 reinterpret_cast<float4*>(dst)[0] = make_float4((float)o[0], (float)o[1], (float)o[2], (float)o[3]);
@@ -312,7 +317,7 @@ int encode_planes(CUtensorMap* tm, void* base, size_t ld8, size_t rows, size_t p
 
 template <int NSL, int CG>
 int launch_pass(Model& m, const CUtensorMap& tm_a, const CUtensorMap& tm_b, int a_plane, int slice0, int mode,
-                size_t rows, cudaStream_t st) {
+                size_t rows, float* out, size_t ld_out, int transposed, cudaStream_t st) {
     constexpr int STAGE = A_STAGE + NSL * CG * KSLAB;
     constexpr int SMEM = STAGES * STAGE + 1024 + 256;
     static bool attr = false;
@@ -326,7 +331,7 @@ int launch_pass(Model& m, const CUtensorMap& tm_a, const CUtensorMap& tm_b, int 
     const int grid = (int)std::min<size_t>((size_t)sms, tiles);
     i8_rotate_kernel<NSL, CG><<<grid, NTHREADS, SMEM, st>>>(tm_a, tm_b, a_plane, slice0, mode, (int)rows, (int)m.n,
                                                            (int)(m.ld8 / KSLAB), m.coef, m.q8_inv_scale, m.q8_rk,
-                                                           m.corr64, m.ld_corr, m.rot, m.ldc);
+                                                           m.corr64, m.ld_corr, out, ld_out, transposed);
     note_launch(1);
     JXB_CUDA_OK(cudaGetLastError());
     return 0;
@@ -335,7 +340,7 @@ int launch_pass(Model& m, const CUtensorMap& tm_a, const CUtensorMap& tm_b, int 
 }  // namespace
 
 // Hand-written tcgen05 path: pass 2 (hom indicator, top 3 slices) -> [pass M (missing indicator)] -> pass D.
-int launch_rotate_int8_tc(Model& m, size_t rows, bool has_missing, cudaStream_t st) {
+int launch_rotate_int8_tc(Model& m, size_t rows, bool has_missing, bool transposed_out, cudaStream_t st) {
     if (rows == 0) return 0;
     const size_t ld_corr = round_up(m.n, 32);
     if (!m.corr64 || m.corr_rows < m.a8_rows || m.ld_corr != ld_corr) {
@@ -359,10 +364,13 @@ int launch_rotate_int8_tc(Model& m, size_t rows, bool has_missing, cudaStream_t 
         if (rc) return rc;
     }
     const CUtensorMap& ta = *(const CUtensorMap*)m.tmap_a8;
-    int rc = launch_pass<3, 64>(m, ta, *(const CUtensorMap*)m.tmap_q8_3, /*a_plane=*/1, /*slice0=*/4, /*mode=*/0, rows, st);
+    int rc = launch_pass<3, 64>(m, ta, *(const CUtensorMap*)m.tmap_q8_3, /*a_plane=*/1, /*slice0=*/4, /*mode=*/0, rows, m.rot, m.ldc, 0, st);
     if (!rc && has_missing)
-        rc = launch_pass<7, 32>(m, ta, *(const CUtensorMap*)m.tmap_q8_7, /*a_plane=*/2, 0, /*mode=*/1, rows, st);
-    if (!rc) rc = launch_pass<7, 32>(m, ta, *(const CUtensorMap*)m.tmap_q8_7, /*a_plane=*/0, 0, /*mode=*/2, rows, st);
+        rc = launch_pass<7, 32>(m, ta, *(const CUtensorMap*)m.tmap_q8_7, /*a_plane=*/2, 0, /*mode=*/1, rows, m.rot, m.ldc, 0, st);
+    // transposed: rotT[n][ldr] with ldr = cap_rows shares the rot allocation (cap_rows * ldc >= n * cap_rows floats)
+    if (!rc)
+        rc = launch_pass<7, 32>(m, ta, *(const CUtensorMap*)m.tmap_q8_7, /*a_plane=*/0, 0, /*mode=*/2, rows, m.rot,
+                                transposed_out ? m.cap_rows : m.ldc, transposed_out ? 1 : 0, st);
     return rc;
 }
 

@@ -36,6 +36,21 @@ int JXB_CAT(k3_solve_blocks_per_sm_p, JXB_P)() {
     return nb < 1 ? 1 : nb;
 }
 
+int JXB_CAT(k3_launch_solve_thread_p, JXB_P)(const k3::ModelView& mv, const float* rotT, size_t ldr, int max_rows,
+                                             const int32_t* n_rows_dev, const SolveParams& sp, double* out,
+                                             int out_cols, int32_t* evals, const void* log_table, cudaStream_t st) {
+    const int blocks = (max_rows + 127) / 128;
+    constexpr int kSmem = 4 * (int)sizeof(k3::ThreadTile<JXB_P>);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k3::solve_thread_kernel<JXB_P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+        attr = true;
+    }
+    k3::solve_thread_kernel<JXB_P><<<blocks, 128, kSmem, st>>>(mv, rotT, ldr, max_rows, n_rows_dev, sp, out, out_cols,
+                                                              evals, (const k3::LogTable*)log_table);
+    return 0;
+}
+
 int JXB_CAT(k3_launch_null_p, JXB_P)(const k3::ModelView& mv, int kind, double low, double high, int max_iter,
                                      double tol, int has_init, double init, double* out_dev, cudaStream_t st) {
     constexpr int kSmem = JXB_K3_BUFS * k3::WarpDims<JXB_P, false>::SMEM_DOUBLES * (int)sizeof(double);

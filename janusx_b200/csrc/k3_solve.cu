@@ -9,7 +9,9 @@ namespace jxb {
                              const SolveParams&, double*, int, int32_t*, int32_t*, cudaStream_t);              \
     int k3_launch_null_p##P(const k3::ModelView&, int, double, double, int, double, int, double, double*,      \
                             cudaStream_t);                                                                     \
-    int k3_solve_blocks_per_sm_p##P();
+    int k3_solve_blocks_per_sm_p##P();                                                                         \
+    int k3_launch_solve_thread_p##P(const k3::ModelView&, const float*, size_t, int, const int32_t*,           \
+                                    const SolveParams&, double*, int, int32_t*, const void*, cudaStream_t);
 JXB_DECL_P(1) JXB_DECL_P(2) JXB_DECL_P(3) JXB_DECL_P(4) JXB_DECL_P(5) JXB_DECL_P(6) JXB_DECL_P(7) JXB_DECL_P(8)
 #undef JXB_DECL_P
 
@@ -81,6 +83,36 @@ int launch_solve(const Model& m, const float* rot, size_t ldc, size_t max_rows, 
     JXB_DISPATCH_P((int)m.p, S_STATIC, S_DYN)
 #undef S_STATIC
 #undef S_DYN
+    JXB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// Large-batch variant: SNP-minor rotated block, one thread per SNP (p <= 8 only).
+int launch_solve_thread(Model& m, const float* rotT, size_t ldr, size_t max_rows, const int32_t* n_rows_dev,
+                        const SolveParams& sp, double* out, int out_cols, int32_t* evals, cudaStream_t st) {
+    if (max_rows == 0) return 0;
+    if (m.p < 1 || m.p > 8) return fail(-2, "thread-per-SNP solve supports 1..8 covariate columns");
+    if (!m.log_table) {
+        // 128-bucket table: c = 1 + (i + 0.5)/128, 1/c rounded, ln c split hi/lo (long double on the host)
+        LogTable h;
+        for (int i = 0; i < 128; ++i) {
+            const long double c = 1.0L + ((long double)i + 0.5L) / 128.0L;
+            h.invc[i] = (double)(1.0L / c);
+            // ln(c) must pair with the ROUNDED 1/c: m * invc - 1 = r  =>  ln m = ln(1+r) - ln(invc)
+            const long double lc = -logl((long double)h.invc[i]);
+            h.logc_hi[i] = (double)lc;
+            h.logc_lo[i] = (double)(lc - (long double)h.logc_hi[i]);
+        }
+        JXB_CUDA_OK(cudaMalloc(&m.log_table, sizeof(LogTable)));
+        JXB_CUDA_OK(cudaMemcpyAsync(m.log_table, &h, sizeof(LogTable), cudaMemcpyHostToDevice, st));
+        JXB_CUDA_OK(cudaStreamSynchronize(st));
+    }
+    const ModelView mv = view_of(m);
+#define T_STATIC(P) k3_launch_solve_thread_p##P(mv, rotT, ldr, (int)max_rows, n_rows_dev, sp, out, out_cols, evals, m.log_table, st)
+#define T_DYN() (void)0
+    JXB_DISPATCH_P((int)m.p, T_STATIC, T_DYN)
+#undef T_STATIC
+#undef T_DYN
     JXB_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -26,6 +26,9 @@ from . import _cabi
 from ._cabi import BedScanCfg, JxbError, QcCfg, SolveCfg, check, lib, ptr
 
 MODEL_CODES = {"add": 0, "dom": 1, "rec": 2, "het": 3}
+# SNP rows per device batch of the file-level scans: one full wave of the thread-per-SNP solve kernel on a
+# 148-SM B200 (148 SMs x 12 warps x 32 SNPs).  The reference's rotate_block_rows (default 512) sizes CPU tiles.
+DEFAULT_DEVICE_BATCH = 56832
 
 __all__ = [
     "DeviceModel", "lmm_reml_chunk_f32", "lmm_reml_chunk_from_snp_f32", "lmm_reml_lmm2_chunk_from_snp_f32",
@@ -383,6 +386,11 @@ def set_rotate_variant(variant: int) -> None:
     lib().jxb_set_rotate_variant(int(variant))
 
 
+def set_thread_solve_min_rows(rows: int) -> None:
+    """Batches with at least `rows` kept SNPs use the one-thread-per-SNP solve kernel (default 32768)."""
+    lib().jxb_set_thread_solve_min_rows(int(rows))
+
+
 def clear_model_cache() -> None:
     while _CACHE:
         _, m = _CACHE.popitem()
@@ -506,7 +514,7 @@ def lmm_reml_assoc_bed_to_tsv_f32(bed_prefix, out_tsv, s, xcov, y_rot, u_t, maf_
     mdl = _get_model(s, xcov, y_rot, u_t)
     return mdl.scan_bed_to_tsv(bed_prefix, out_tsv, maf_thr, miss_thr, het_thr, genetic_model, snps_only, sample_ids,
                                "lmm", low, high, max_iter, tol, nullml, None, None,
-                               batch_rows=max(int(rotate_block_rows), 4096), progress_callback=progress_callback,
+                               batch_rows=max(int(rotate_block_rows), DEFAULT_DEVICE_BATCH), progress_callback=progress_callback,
                                progress_every=progress_every)
 
 
@@ -537,7 +545,7 @@ def lmm_reml_lmm2_assoc_bed_to_tsv_f32(bed_prefix, out_tsv, s, xcov, y_rot, u_t,
     init = i_reml if i_reml is not None else i_ml
     return mdl.scan_bed_to_tsv(bed_prefix, out_tsv, maf_thr, miss_thr, het_thr, genetic_model, snps_only, sample_ids,
                                "lmm2", low, high, max_iter, tol, nullml, init, None,
-                               batch_rows=max(int(rotate_block_rows), 4096), progress_callback=progress_callback,
+                               batch_rows=max(int(rotate_block_rows), DEFAULT_DEVICE_BATCH), progress_callback=progress_callback,
                                progress_every=progress_every)
 
 
@@ -555,7 +563,7 @@ def fvlmm_assoc_bed_to_tsv_f32(bed_prefix, out_tsv, s, xcov, y_rot, log10_lbd, u
     mdl = _get_model(s, xcov, y_rot, u_t)
     rows = mdl.scan_bed_to_tsv(bed_prefix, out_tsv, maf_thr, miss_thr, het_thr, genetic_model, snps_only, sample_ids,
                                "fvlmm", nullml=nullml, log10_lbd=log10_lbd,
-                               batch_rows=max(int(rotate_block_rows), 4096), progress_callback=progress_callback,
+                               batch_rows=max(int(rotate_block_rows), DEFAULT_DEVICE_BATCH), progress_callback=progress_callback,
                                progress_every=progress_every)
     # fvlmm.rs:2746-2753: pve = clamp(1 - ypy / sum y^2, 0, 1)
     _, meta = mdl.fixed_chunk(np.zeros((1, mdl.n), dtype=np.float32), log10_lbd, rotated=True, return_meta=True)

@@ -365,3 +365,36 @@ def test_int8_sliced_rotation_variant(jx, oracle):
             assert np.array_equal(d2, d0, equal_nan=True)
     finally:
         jx.set_rotate_variant(3)
+
+
+@pytest.mark.parametrize("mode", ["lmm", "lmm2"])
+def test_thread_per_snp_solve_kernel(jx, oracle, mode):
+    """The large-batch path (tcgen05 rotation writing an SNP-minor block + one thread per SNP with the
+    table-driven log) must satisfy the same gates as the warp kernel."""
+    case = make_problem(n=450, m=500, q=3, seed=411, missing_rate=0.02)
+    nm = null_model(oracle, case)
+    n = case.n
+    keep, af, mr, missing = oracle.count_qc_block(case.packed, n, None, 0.02, 0.05, 1.0)
+    idx = np.nonzero(keep)[0]
+    g = oracle.decode_centered_block(case.packed, n, af[idx], row_indices=idx)
+    mdl = jx.DeviceModel(case.s, nm["xcov"], nm["y"], nm["ut"])
+    try:
+        jx.set_thread_solve_min_rows(1)
+        if mode == "lmm":
+            want = oracle.lmm_reml_chunk_from_snp_f32(case.s, nm["xcov"], nm["y"], nm["low"], nm["high"], g, nm["ut"], 30, 1e-2)
+            k, _, _, out, ev = mdl.scan_packed(case.packed, n, low=nm["low"], high=nm["high"], return_evals=True)
+            assert_results_close(out, want)
+        else:
+            _, mlnull = oracle.lmm_ml_null_brent(case.s, nm["xcov"], nm["y"], nm["low"], nm["high"], 30, 1e-2)
+            want = oracle.lmm_reml_lmm2_chunk_from_snp_f32(case.s, nm["xcov"], nm["y"], nm["low"], nm["high"], g, nm["ut"], mlnull, 30, 1e-2)
+            k, _, _, out = mdl.scan_packed(case.packed, n, mode="lmm2", low=nm["low"], high=nm["high"], nullml=mlnull)
+            assert_results_close(out, want, cols_p=(2, 5), cols_lambda=(3,))
+            np.testing.assert_allclose(out[:, 4], want[:, 4], rtol=1e-10)
+        assert np.array_equal(k, keep)
+        # switching back to the warp kernel on the same model (row-major block) still works
+        jx.set_thread_solve_min_rows(1 << 30)
+        out_w = mdl.scan_packed(case.packed, n, mode=mode, low=nm["low"], high=nm["high"],
+                                nullml=(mlnull if mode == "lmm2" else None))[3]
+        assert_results_close(out_w, want, cols_p=((2, 5) if mode == "lmm2" else (2,)))
+    finally:
+        jx.set_thread_solve_min_rows(32768)
