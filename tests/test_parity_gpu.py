@@ -398,3 +398,79 @@ def test_thread_per_snp_solve_kernel(jx, oracle, mode):
         assert_results_close(out_w, want, cols_p=((2, 5) if mode == "lmm2" else (2,)))
     finally:
         jx.set_thread_solve_min_rows(32768)
+
+
+def test_full_size_n20000_parity_sample(jx, oracle):
+    """BASELINE.json configs[2] sample count (n = 20,000, 3 covariates, LMM2): a 96-SNP sample through the
+    bench path (tcgen05 int8 rotation + thread-per-SNP solve) and through the FP64 DMMA + warp-solve path, both
+    against the CPU oracle at the north-star gates."""
+    import torch
+    sys_path_bench = __import__("sys").path
+    from pathlib import Path
+    root = str(Path(__file__).resolve().parents[1])
+    if root not in sys_path_bench:
+        sys_path_bench.insert(0, root)
+    import bench as B
+    n, m, q = 20000, 96, 3
+    dev = torch.device("cuda:0")
+    s_np, u_t_dev, X_np, y_np = B.build_null_model(torch, n, 4096, q, dev)
+    ut = u_t_dev.cpu().numpy()
+    pk, _ = B.gen_packed_batch(torch, n, m, 777, dev)
+    packed = pk.cpu().numpy()
+    packed[5, :40] = 0b01010101          # a few missing calls -> exercises the missing-indicator pass
+    mdl = jx.DeviceModel(s_np, np.ones((n, q + 1)), np.zeros(n), u_t_dev, device=0, u_t_on_device=True)
+    del u_t_dev
+    xcov, yrot = mdl.rotate_xy(X_np, y_np)
+    xo, yo = oracle.lmm_rotate_x_y_with_ut_f64(ut, X_np, y_np)
+    np.testing.assert_allclose(xcov, xo, rtol=1e-10, atol=1e-11)
+    # use the ORACLE's rotated design on both sides so the comparison isolates the scan
+    mdl.set_xy(xo, yo[:, 0])
+    lbd, ml0, reml0 = mdl.reml_null(-5.0, 5.0, 50, 1e-3)
+    lbd_o, ml0_o, reml0_o = oracle.lmm_reml_null_f32(s_np, xo, yo[:, 0], -5.0, 5.0, 50, 1e-3)
+    assert math.isclose(lbd, lbd_o, rel_tol=RTOL_LAMBDA) and math.isclose(reml0, reml0_o, rel_tol=1e-10)
+    l10 = float(np.log10(lbd_o))
+    lo, hi = l10 - 2.0, l10 + 2.0
+    _, nullml = oracle.lmm_ml_null_brent(s_np, xo, yo[:, 0], lo, hi, 30, 1e-2, l10)
+    keep, af, mr, missing = oracle.count_qc_block(packed, n, None, 0.02, 0.05, 1.0)
+    idx = np.nonzero(keep)[0]
+    g = oracle.decode_centered_block(packed, n, af[idx], row_indices=idx)
+    want = oracle.lmm_reml_lmm2_chunk_f32(s_np, xo, yo[:, 0], lo, hi, oracle.rotate_block(g, ut), nullml, 30, 1e-2,
+                                          init_reml=l10)
+    kw = dict(mode="lmm2", low=lo, high=hi, init=l10, nullml=nullml)
+    try:
+        jx.set_thread_solve_min_rows(1)
+        k1, af1, ms1, out1 = mdl.scan_packed(packed, n, **kw)          # tcgen05 + thread kernel (bench path)
+        jx.set_thread_solve_min_rows(1 << 30)
+        k2, _, _, out2 = mdl.scan_packed(packed, n, **kw)                # tcgen05 + warp kernel
+        jx.set_rotate_variant(0)
+        k3, _, _, out3 = mdl.scan_packed(packed, n, **kw)                # FP64 DMMA + warp kernel
+    finally:
+        jx.set_rotate_variant(3)
+        jx.set_thread_solve_min_rows(32768)
+    assert np.array_equal(k1, keep) and np.array_equal(ms1, missing)
+    assert np.array_equal(af1.view(np.uint32), af.view(np.uint32))
+    for out in (out1, out2, out3):
+        assert_results_close(out, want, cols_p=(2, 5), cols_lambda=(3,))
+        np.testing.assert_allclose(out[:, 4], want[:, 4], rtol=1e-10)
+
+
+def test_cli_gwas_lmm_end_to_end(jx, oracle, tmp_path):
+    """`python -m janusx_b200.gwas` with the reference's flag names writes the reference TSV schema and naming;
+    rows agree with the oracle run on the same null model."""
+    from janusx_b200 import gwas, synth
+    case = make_problem(n=200, m=300, q=0, seed=88, missing_rate=0.02)
+    prefix = str(tmp_path / "panel")
+    synth.write_plink(prefix, case.packed, case.n)
+    with open(tmp_path / "pheno.tsv", "w") as fh:
+        fh.write("id\ttraitA\n")
+        for j in range(case.n):
+            fh.write(f"S{j}\t{case.y[j]:.10f}\n" if j != 7 else f"S{j}\tNA\n")   # one missing phenotype
+    rc = gwas.main(["-bfile", prefix, "-p", str(tmp_path / "pheno.tsv"), "-n", "0", "-lmm", "-lmm2", "-fvlmm",
+                    "-k", "1", "-o", str(tmp_path / "out"), "-prefix", "run"])
+    assert rc == 0
+    for model, ncols in (("lmm", 11), ("lmm2", 14), ("fvlmm", 11)):
+        lines = (tmp_path / "out" / f"run.traitA.{model}.tsv").read_text().splitlines()
+        assert lines[0].split("\t")[:5] == ["chrom", "pos", "snp", "allele0", "allele1"]
+        assert len(lines[0].split("\t")) == ncols and len(lines) > 100
+        assert all(len(l.split("\t")) == ncols for l in lines[1:])
+    assert not list((tmp_path / "out").glob("*.tmp"))
