@@ -177,7 +177,6 @@ int ensure_capacity(jxb_model* h, size_t rows, size_t bps, bool need_g) {
         if (m.packed) { cudaFree(m.packed); m.packed = nullptr; m.bps_cap = 0; }
         if (rc) return rc;
         m.cap_rows = cap;
-        m.ldr = cap;
     }
     if (need_g && !m.g64) {
         JXB_CUDA_OK(cudaMalloc((void**)&m.g64, m.cap_rows * m.ldk * sizeof(double)));
@@ -481,7 +480,7 @@ void jxb_model_destroy(jxb_model* h) {
     Model& m = h->m;
     cudaSetDevice(m.device);
     if (m.stream) cudaStreamSynchronize(m.stream);
-    void* ptrs[] = {m.s, m.y, m.xt, m.rec, m.ut, m.g64, m.rot, m.rotT, m.out, m.evals, m.packed, m.counts, m.af, m.src_row,
+    void* ptrs[] = {m.s, m.y, m.xt, m.rec, m.ut, m.g64, m.rot, m.log_table, m.out, m.evals, m.packed, m.counts, m.af, m.src_row,
                     m.n_kept, m.sample_idx, m.stage_f32, m.fx_w, m.fx_py, m.fx_wx, m.fx_scal, h->missr, h->mask,
                     h->scal, m.q8, m.q8_inv_scale, m.q8_rk, m.a8, m.coef, m.flags8, m.c32, m.lt_ws, m.corr64};
     for (void* p : ptrs)

@@ -50,9 +50,8 @@ struct Model {
     // scan workspace (grown on demand)
     size_t cap_rows = 0;
     double* g64 = nullptr;     // [cap_rows_pad][ldk] decoded+centred genotypes (GEMM A operand)
-    float* rotT = nullptr;     // [n][ldr]  rotated genotypes, f32 (reference storage type), SNP-minor for K3
-    size_t ldr = 0;            // = cap_rows
-    float* rot = nullptr;      // [cap_rows][ldc] row-major rotated block (only for jxb_rotate_block_f32), lazy
+    float* rot = nullptr;      // rotated block, f32 (reference storage type): row-major [cap_rows][ldc] for the warp
+                               // solve kernel, or viewed SNP-minor [round_up(n,32)][cap_rows] for the thread kernel
     size_t ldc = 0;
     double* out = nullptr;     // [cap_rows][8]
     int32_t* evals = nullptr;  // [cap_rows]
