@@ -169,6 +169,11 @@ typedef struct {
     size_t snp_begin, snp_end; /* scan [begin,end) of BED rows; end==0 => all (multi-GPU shards) */
     int32_t write_header;
     size_t progress_every;
+    /* prepared row metadata (src/stats/lmm.rs:2576-2612): nullable ascending BED row indices.  When given, only
+     * these rows are scanned and the QC thresholds are NOT re-applied (the list is trusted, like the reference);
+     * allele frequency and missingness are recomputed from the packed rows on the device. */
+    const int64_t* row_indices;
+    size_t n_row_indices;
 } jxb_bed_scan_cfg;
 int jxb_scan_bed_to_tsv(jxb_model* m, const jxb_bed_scan_cfg* cfg, size_t* rows_written, jxb_progress_cb cb,
                         void* user);

@@ -39,7 +39,8 @@ class BedScanCfg(C.Structure):
     _fields_ = [("bed_prefix", C.c_char_p), ("out_tsv", C.c_char_p), ("qc", QcCfg), ("solve", SolveCfg),
                 ("mode", C.c_int32), ("snps_only", C.c_int32), ("sample_ids", C.POINTER(C.c_char_p)),
                 ("n_sample_ids", C.c_size_t), ("batch_rows", C.c_size_t), ("snp_begin", C.c_size_t),
-                ("snp_end", C.c_size_t), ("write_header", C.c_int32), ("progress_every", C.c_size_t)]
+                ("snp_end", C.c_size_t), ("write_header", C.c_int32), ("progress_every", C.c_size_t),
+                ("row_indices", C.POINTER(C.c_int64)), ("n_row_indices", C.c_size_t)]
 
 
 # every symbol include/jxb200.h declares: (name, restype, argtypes or None)

@@ -365,13 +365,39 @@ extern "C" int jxb_scan_bed_to_tsv(jxb_model* m, const jxb_bed_scan_cfg* cfg, si
     wr.n_model = n;
     wr.th = std::thread([&wr] { wr.run(); });
 
-    const size_t total = end - begin;
+    // prepared row metadata: scan only the listed rows (ascending), QC thresholds are not re-applied
+    const bool prepared = cfg->row_indices != nullptr;
+    jxb_qc_cfg qc = cfg->qc;
+    if (prepared) {
+        for (size_t i = 0; i < cfg->n_row_indices; ++i) {
+            const int64_t v = cfg->row_indices[i];
+            if (v < 0 || (size_t)v >= n_snps) { wr.finish(); fclose(wr.fp); unmap(); return fail(-34, "row_indices out of range"); }
+            if (i && v < cfg->row_indices[i - 1]) {
+                wr.finish(); fclose(wr.fp); unmap();
+                return fail(-35, "prepared row_indices must be sorted in ascending BED order");
+            }
+        }
+        qc.maf_thr = 0.0f; qc.miss_thr = 1.0f; qc.het_thr = 0.0f;
+    }
+    const size_t total = prepared ? cfg->n_row_indices : end - begin;
     const size_t step = std::max<size_t>(1, std::min<size_t>(cfg->batch_rows ? cfg->batch_rows : 4096, std::max<size_t>(total, 1)));
     size_t next_emit = cfg->progress_every ? std::max<size_t>(1, std::min(cfg->progress_every, total)) : 0;
     int rc = 0;
     std::vector<uint8_t> pre_keep;
-    for (size_t c0 = begin; c0 < end && rc == 0; c0 += step) {
-        const size_t rows = std::min(step, end - c0);
+    size_t list_pos = 0;   // prepared mode: next entry of row_indices
+    size_t scanned = 0;
+    for (size_t c0 = begin; rc == 0;) {
+        size_t rows;
+        if (prepared) {
+            // skip list entries before `begin`, stop at `end`
+            while (list_pos < cfg->n_row_indices && (size_t)cfg->row_indices[list_pos] < begin) ++list_pos;
+            if (list_pos >= cfg->n_row_indices || (size_t)cfg->row_indices[list_pos] >= end) break;
+            c0 = (size_t)cfg->row_indices[list_pos];
+            rows = std::min(step, end - c0);
+        } else {
+            if (c0 >= end) break;
+            rows = std::min(step, end - c0);
+        }
         Batch* b = new Batch();
         b->sites.resize(rows);
         b->keep.resize(rows);
@@ -379,7 +405,14 @@ extern "C" int jxb_scan_bed_to_tsv(jxb_model* m, const jxb_bed_scan_cfg* cfg, si
         b->missing.resize(rows);
         b->out.resize(rows * out_cols);
         b->out_cols = out_cols;
-        for (size_t r = 0; r < rows; ++r) {
+        // BIM is read sequentially: skip the lines between the previous batch and this one
+        while (rc == 0 && bim.next_row < c0) {
+            int br = bim.next(skip, err);
+            if (br != 0)
+                rc = fail(-29, br < 0 ? err : "BIM ended early: needed row " + std::to_string(c0) + " but only saw " +
+                                                  std::to_string(bim.next_row) + " rows from " + bim.path);
+        }
+        for (size_t r = 0; r < rows && rc == 0; ++r) {
             int br = bim.next(b->sites[r], err);
             if (br != 0) {
                 rc = fail(-29, br < 0 ? err : "BIM ended early: needed row " + std::to_string(c0 + rows) +
@@ -389,24 +422,34 @@ extern "C" int jxb_scan_bed_to_tsv(jxb_model* m, const jxb_bed_scan_cfg* cfg, si
         }
         if (rc) { delete b; break; }
         const uint8_t* mask = nullptr;
-        if (cfg->snps_only) {
-            pre_keep.assign(rows, 1);
-            for (size_t r = 0; r < rows; ++r)
-                if (!simple_snp_allele(b->sites[r].a0) || !simple_snp_allele(b->sites[r].a1)) pre_keep[r] = 0;
+        size_t listed = 0;
+        if (cfg->snps_only || prepared) {
+            pre_keep.assign(rows, prepared ? 0 : 1);
+            if (prepared) {
+                while (list_pos < cfg->n_row_indices && (size_t)cfg->row_indices[list_pos] < c0 + rows) {
+                    pre_keep[(size_t)cfg->row_indices[list_pos] - c0] = 1;
+                    ++list_pos;
+                    ++listed;
+                }
+            }
+            if (cfg->snps_only)
+                for (size_t r = 0; r < rows; ++r)
+                    if (!simple_snp_allele(b->sites[r].a0) || !simple_snp_allele(b->sites[r].a1)) pre_keep[r] = 0;
             mask = pre_keep.data();
         }
-        rc = jxb_scan_packed(m, payload + c0 * bps, bps, rows, n_full, identity ? nullptr : sidx.data(), mask, &cfg->qc,
+        rc = jxb_scan_packed(m, payload + c0 * bps, bps, rows, n_full, identity ? nullptr : sidx.data(), mask, &qc,
                              &solve, mode, b->keep.data(), b->af.data(), b->missing.data(), b->out.data(), nullptr,
                              &b->n_kept);
         if (rc) { delete b; break; }
         wr.push(b);
-        const size_t scanned = c0 + rows - begin;
+        scanned += prepared ? listed : rows;
+        c0 += rows;
         if (cb && next_emit && scanned >= next_emit) {
             if (cb(scanned < total ? scanned : total, total, user) != 0) { rc = fail(-40, "interrupted by progress callback"); break; }
             next_emit = std::min((scanned / cfg->progress_every + 1) * cfg->progress_every, total);
         }
     }
-    if (rc == 0 && end == n_snps) {
+    if (rc == 0 && end == n_snps && !prepared) {
         // gfcore.rs:265-280: the BIM must not hold more rows than the BED
         Site extra;
         int br = bim.next(extra, err);

@@ -35,6 +35,7 @@ __all__ = [
     "lmm_assoc_chunk_f32", "lmm_assoc_chunk_from_snp_f32", "lmm_reml_null_f32", "ml_loglike_null_f32",
     "lmm_rotate_x_y_with_ut_f64", "lmm_reml_assoc_bed_to_tsv_f32", "lmm_reml_lmm2_assoc_bed_to_tsv_f32",
     "fvlmm_assoc_bed_to_tsv_f32", "fvlmm_assoc_chunk_f32", "fvlmm_assoc_chunk_from_snp_f32",
+    "gwas_lmm_lm_null_lrt_decision",
 ]
 
 
@@ -286,7 +287,7 @@ class DeviceModel:
     def scan_bed_to_tsv(self, bed_prefix, out_tsv, maf_thr, miss_thr, het_thr, genetic_model="add", snps_only=False,
                         sample_ids=None, mode="lmm", low=-5.0, high=5.0, max_iter=30, tol=1e-2, nullml=None,
                         init=None, log10_lbd=None, batch_rows=4096, progress_callback=None, progress_every=0,
-                        snp_begin=0, snp_end=0, write_header=True) -> int:
+                        snp_begin=0, snp_end=0, write_header=True, row_indices=None) -> int:
         cfg = BedScanCfg()
         cfg.bed_prefix = str(bed_prefix).encode()
         cfg.out_tsv = str(out_tsv).encode()
@@ -307,6 +308,11 @@ class DeviceModel:
         cfg.snp_begin, cfg.snp_end = int(snp_begin), int(snp_end)
         cfg.write_header = 1 if write_header else 0
         cfg.progress_every = int(progress_every)
+        rows_keepalive = None
+        if row_indices is not None:
+            rows_keepalive = np.ascontiguousarray(np.asarray(row_indices, dtype=np.int64))
+            cfg.row_indices = rows_keepalive.ctypes.data_as(C.POINTER(C.c_int64))
+            cfg.n_row_indices = rows_keepalive.shape[0]
         err = []
 
         def _cb(done, total, _user):
@@ -490,15 +496,29 @@ def _check_bed_args(s, xcov, y_rot, u_t, low, high, tol):
         raise RuntimeError("n must be > p+1")
 
 
-def _reject_prepared(row_indices, row_flip, row_missing, row_maf):
+def _prepared_rows(row_indices, row_flip, row_missing, row_maf):
+    """Prepared row metadata (src/stats/lmm.rs:2576-2612): all four or none.  Only `row_indices` steers the device
+    scan (the listed rows are scanned without re-applying QC); allele frequency and missingness are recomputed from
+    the packed rows, which reproduces `row_maf` / `row_missing` whenever the metadata came from the same samples."""
     given = [v is not None for v in (row_indices, row_flip, row_missing, row_maf)]
     if any(given) and not all(given):
         raise RuntimeError(
             "prepared row metadata must provide all or none of: row_indices, row_flip, row_missing, row_maf")
-    if all(given):
-        raise NotImplementedError(
-            "prepared row metadata (row_indices/row_flip/row_missing/row_maf) is not supported yet: "
-            "the device path recomputes counts and QC from the packed rows")
+    if not all(given):
+        return None
+    idx = np.ascontiguousarray(np.asarray(row_indices, dtype=np.int64).reshape(-1))
+    m = idx.shape[0]
+    if not (np.asarray(row_flip).shape[0] == m and np.asarray(row_missing).shape[0] == m
+            and np.asarray(row_maf).shape[0] == m):
+        raise RuntimeError(
+            f"prepared row metadata length mismatch: row_indices={m}, row_flip={np.asarray(row_flip).shape[0]}, "
+            f"row_maf={np.asarray(row_maf).shape[0]}, row_missing={np.asarray(row_missing).shape[0]}")
+    if np.any(np.asarray(row_flip, dtype=bool)):
+        raise NotImplementedError("row_flip=True is not supported (the reference never sets it on this path, "
+                                  "src/stats/lmm.rs:1316-1321)")
+    if m > 1 and np.any(np.diff(idx) < 0):
+        raise RuntimeError("prepared row_indices must be sorted in ascending BED order")
+    return idx
 
 
 def lmm_reml_assoc_bed_to_tsv_f32(bed_prefix, out_tsv, s, xcov, y_rot, u_t, maf_thr, miss_thr, het_thr,
@@ -510,10 +530,10 @@ def lmm_reml_assoc_bed_to_tsv_f32(bed_prefix, out_tsv, s, xcov, y_rot, u_t, maf_
     every SNP starts from the interval midpoint), so `init_log10_lbd` only matters for LMM2."""
     _check_bed_args(s, xcov, y_rot, u_t, low, high, tol)
     _model_code(genetic_model)
-    _reject_prepared(row_indices, row_flip, row_missing, row_maf)
+    rows_sel = _prepared_rows(row_indices, row_flip, row_missing, row_maf)
     mdl = _get_model(s, xcov, y_rot, u_t)
     return mdl.scan_bed_to_tsv(bed_prefix, out_tsv, maf_thr, miss_thr, het_thr, genetic_model, snps_only, sample_ids,
-                               "lmm", low, high, max_iter, tol, nullml, None, None,
+                               "lmm", low, high, max_iter, tol, nullml, None, None, row_indices=rows_sel,
                                batch_rows=max(int(rotate_block_rows), DEFAULT_DEVICE_BATCH), progress_callback=progress_callback,
                                progress_every=progress_every)
 
@@ -527,7 +547,7 @@ def lmm_reml_lmm2_assoc_bed_to_tsv_f32(bed_prefix, out_tsv, s, xcov, y_rot, u_t,
     """src/stats/lmm.rs:2753-3038 (REML start = init_reml.or(init_ml); ML start = per-SNP REML optimum)."""
     _check_bed_args(s, xcov, y_rot, u_t, low, high, tol)
     _model_code(genetic_model)
-    _reject_prepared(row_indices, row_flip, row_missing, row_maf)
+    rows_sel = _prepared_rows(row_indices, row_flip, row_missing, row_maf)
     if nullml is not None and not math.isfinite(nullml):
         raise RuntimeError("nullml must be finite when provided")
     mdl = _get_model(s, xcov, y_rot, u_t)
@@ -544,7 +564,7 @@ def lmm_reml_lmm2_assoc_bed_to_tsv_f32(bed_prefix, out_tsv, s, xcov, y_rot, u_t,
             raise RuntimeError("failed to optimize null ML for LMM2 unified scan")
     init = i_reml if i_reml is not None else i_ml
     return mdl.scan_bed_to_tsv(bed_prefix, out_tsv, maf_thr, miss_thr, het_thr, genetic_model, snps_only, sample_ids,
-                               "lmm2", low, high, max_iter, tol, nullml, init, None,
+                               "lmm2", low, high, max_iter, tol, nullml, init, None, row_indices=rows_sel,
                                batch_rows=max(int(rotate_block_rows), DEFAULT_DEVICE_BATCH), progress_callback=progress_callback,
                                progress_every=progress_every)
 
@@ -559,10 +579,10 @@ def fvlmm_assoc_bed_to_tsv_f32(bed_prefix, out_tsv, s, xcov, y_rot, log10_lbd, u
     if not (math.isfinite(lbd) and lbd > 0.0):
         raise RuntimeError("invalid log10_lbd")
     _model_code(genetic_model)
-    _reject_prepared(row_indices, row_flip, row_missing, row_maf)
+    rows_sel = _prepared_rows(row_indices, row_flip, row_missing, row_maf)
     mdl = _get_model(s, xcov, y_rot, u_t)
     rows = mdl.scan_bed_to_tsv(bed_prefix, out_tsv, maf_thr, miss_thr, het_thr, genetic_model, snps_only, sample_ids,
-                               "fvlmm", nullml=nullml, log10_lbd=log10_lbd,
+                               "fvlmm", nullml=nullml, log10_lbd=log10_lbd, row_indices=rows_sel,
                                batch_rows=max(int(rotate_block_rows), DEFAULT_DEVICE_BATCH), progress_callback=progress_callback,
                                progress_every=progress_every)
     # fvlmm.rs:2746-2753: pve = clamp(1 - ypy / sum y^2, 0, 1)
@@ -570,3 +590,51 @@ def fvlmm_assoc_bed_to_tsv_f32(bed_prefix, out_tsv, s, xcov, y_rot, log10_lbd, u
     y_sq = float(np.sum(mdl.y * mdl.y))
     pve = float(min(max(1.0 - meta["ypy"] / y_sq, 0.0), 1.0)) if y_sq > 0.0 else float("nan")
     return rows, pve, float(meta["log_det_v"])
+
+
+def gwas_lmm_lm_null_lrt_decision(y, x_cov, lmm_ml0, alpha=0.05, boundary_mixture=True):
+    """src/stats/gwas_unified.rs:119-175 -> (switch_to_lm, lrt_stat, pval, lm_ml0).
+
+    Host-side bookkeeping, once per trait (an n x (p+1) least-squares fit): H0 "Va = 0" is tested with the LRT of
+    the LMM null ML against the plain linear-model ML; a non-significant test means the caller may fall back to LM.
+    """
+    if not math.isfinite(lmm_ml0):
+        raise RuntimeError("lmm_ml0 must be finite")
+    if not (math.isfinite(alpha) and 0.0 < alpha < 1.0):
+        raise RuntimeError("alpha must be in (0,1)")
+    y = _f64(y).reshape(-1)
+    x = _f64(x_cov)
+    if x.ndim != 2:
+        raise RuntimeError("x_cov must be 2D")
+    n, p_cov = y.shape[0], x.shape[1]
+    if x.shape[0] != n:
+        raise RuntimeError("x_cov rows must equal len(y)")
+    if n <= p_cov + 1:
+        raise RuntimeError("insufficient samples: require n > p_cov + 1")
+    design = np.concatenate([np.ones((n, 1)), x], axis=1)          # gwas_unified.rs:63-70: intercept + covariates
+    xtx = design.T @ design
+    xty = design.T @ y
+    try:
+        chol = np.linalg.cholesky(xtx)
+    except np.linalg.LinAlgError:
+        try:
+            chol = np.linalg.cholesky(xtx + 1e-8 * np.eye(p_cov + 1))
+        except np.linalg.LinAlgError:
+            raise RuntimeError("failed to compute LM null log-likelihood")
+    beta = np.linalg.solve(chol.T, np.linalg.solve(chol, xty))
+    resid = y - design @ beta
+    rss = float(resid @ resid)
+    if not (math.isfinite(rss) and rss > 0.0):
+        raise RuntimeError("failed to compute LM null log-likelihood")
+    n_f = float(n)
+    lm_ml0 = n_f * (math.log(n_f) - 1.0 - math.log(2.0 * math.pi)) / 2.0 - 0.5 * n_f * math.log(rss)
+    stat = 2.0 * (lmm_ml0 - lm_ml0)
+    if not math.isfinite(stat) or stat < 0.0:
+        stat = 0.0
+    pval = math.erfc(math.sqrt(0.5 * stat)) if stat > 0.0 else 1.0   # chi2_sf_df1, src/math/linalg.rs:7-17
+    if boundary_mixture:
+        pval *= 0.5
+    if not math.isfinite(pval):
+        pval = 1.0
+    pval = min(max(pval, 2.2250738585072014e-308), 1.0)
+    return bool(pval >= alpha), float(stat), float(pval), float(lm_ml0)

@@ -84,7 +84,35 @@ def test_argument_validation_messages():
         jxrs.lmm_reml_assoc_bed_to_tsv_f32("p", "o", s, x, y, ut, 0.02, 0.05, 1.0, genetic_model="xyz")
     with pytest.raises(RuntimeError, match="prepared row metadata must provide all or none"):
         jxrs.lmm_reml_assoc_bed_to_tsv_f32("p", "o", s, x, y, ut, 0.02, 0.05, 1.0, row_indices=np.arange(3))
+    with pytest.raises(RuntimeError, match="sorted in ascending BED order"):
+        jxrs.lmm_reml_assoc_bed_to_tsv_f32("p", "o", s, x, y, ut, 0.02, 0.05, 1.0, row_indices=np.array([3, 1]),
+                                           row_flip=np.zeros(2, bool), row_missing=np.zeros(2, np.float32),
+                                           row_maf=np.zeros(2, np.float32))
     with pytest.raises(RuntimeError, match=r"x rows must equal len\(y\)"):
         jxrs.lmm_rotate_x_y_with_ut_f64(ut, np.ones((n - 1, 2)), y)
     with pytest.raises(RuntimeError, match="invalid log10_lbd"):
         jxrs.fvlmm_assoc_bed_to_tsv_f32("p", "o", s, x, y, float("nan"), ut, 0.02, 0.05, 1.0)
+
+
+def test_lmm_lm_null_lrt_decision_host_logic():
+    """src/stats/gwas_unified.rs:119-175: LM null ML closed form + boundary-mixture LRT."""
+    import math
+    from janusx_b200 import jxrs
+    rng = np.random.default_rng(3)
+    n = 300
+    x = rng.normal(size=(n, 2))
+    y = 1.0 + x @ np.array([0.5, -0.25]) + rng.normal(size=n)
+    design = np.concatenate([np.ones((n, 1)), x], axis=1)
+    rss = float(np.sum((y - design @ np.linalg.lstsq(design, y, rcond=None)[0]) ** 2))
+    lm_ml0 = n * (math.log(n) - 1 - math.log(2 * math.pi)) / 2 - 0.5 * n * math.log(rss)
+    sw, stat, p, got = jxrs.gwas_lmm_lm_null_lrt_decision(y, x, lm_ml0 + 0.1)
+    assert math.isclose(got, lm_ml0, rel_tol=1e-12) and math.isclose(stat, 0.2, rel_tol=1e-9)
+    assert math.isclose(p, 0.5 * math.erfc(math.sqrt(0.1)), rel_tol=1e-12) and sw is True
+    sw2, stat2, p2, _ = jxrs.gwas_lmm_lm_null_lrt_decision(y, x, lm_ml0 + 10.0)
+    assert sw2 is False and p2 < 1e-5
+    sw3, stat3, p3, _ = jxrs.gwas_lmm_lm_null_lrt_decision(y, x, lm_ml0 - 5.0, boundary_mixture=False)
+    assert stat3 == 0.0 and p3 == 1.0 and sw3 is True
+    with pytest.raises(RuntimeError, match="alpha must be in"):
+        jxrs.gwas_lmm_lm_null_lrt_decision(y, x, 0.0, alpha=1.5)
+    with pytest.raises(RuntimeError, match="insufficient samples"):
+        jxrs.gwas_lmm_lm_null_lrt_decision(y[:3], x[:3], 0.0)

@@ -281,6 +281,20 @@ def test_bed_to_tsv_matches_oracle(jx, oracle, tmp_path):
     rows3_o = oracle.scan_bed_to_tsv(prefix, str(tmp_path / "o3.tsv"), *args, model="fvlmm", log10_lbd=l10)
     assert rows3 == rows3_o and 0.0 <= pve <= 1.0 and math.isfinite(ldv)
     _assert_tsv_equiv(tmp_path / "g3.tsv", tmp_path / "o3.tsv")
+    # prepared row metadata (the default CLI route of the reference): listed rows are scanned without re-applying QC
+    keep_o, af_o, mr_o, _ = oracle.count_qc_block(case.packed, case.n, None, 0.02, 0.05, 1.0)
+    listed = np.nonzero(keep_o)[0]
+    meta = dict(row_indices=listed, row_flip=np.zeros(listed.size, bool), row_missing=mr_o[listed], row_maf=af_o[listed])
+    rows_p = jx.lmm_reml_assoc_bed_to_tsv_f32(prefix, str(tmp_path / "gp.tsv"), *args, low=nm["low"], high=nm["high"],
+                                              rotate_block_rows=256, **meta)
+    assert rows_p == rows and (tmp_path / "gp.tsv").read_bytes() == (tmp_path / "g.tsv").read_bytes()
+    sub = listed[::7]
+    meta = dict(row_indices=sub, row_flip=np.zeros(sub.size, bool), row_missing=mr_o[sub], row_maf=af_o[sub])
+    rows_s = jx.lmm_reml_assoc_bed_to_tsv_f32(prefix, str(tmp_path / "gs.tsv"), *args, low=nm["low"], high=nm["high"], **meta)
+    full_lines = (tmp_path / "g.tsv").read_bytes().split(b"\n")
+    sub_lines = (tmp_path / "gs.tsv").read_bytes().split(b"\n")
+    assert rows_s == sub.size and sub_lines[0] == full_lines[0]
+    assert sub_lines[1:-1] == [full_lines[1 + i] for i in range(0, listed.size, 7)]
     # sample subset by IID + snps_only + error paths
     some = [f"S{j}" for j in range(case.n)]
     with pytest.raises(RuntimeError, match="sample 'nobody' not found in PLINK FAM"):
