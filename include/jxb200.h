@@ -183,6 +183,54 @@ int jxb_scan_bed_to_tsv(jxb_model* m, const jxb_bed_scan_cfg* cfg, size_t* rows_
 size_t jxb_format_row(char* buf, size_t cap, const char* chrom, int64_t pos, const char* snp, const char* a0,
                       const char* a1, float af, float miss_rate, const double* row, int out_cols);
 
+/* Block formatter behind GwasAssocTsvWriter.write_chunk (src/io/assoc2tsv.rs:789-860, append_assoc_row_text
+ * :364-428): `rows` result rows; every string column is one blob of `rows` NUL-terminated strings; genetic_model
+ * 0..3 = add/dom/rec/het applies transform_alleles_by_model (:117-137).  Returns the bytes the block needs; nothing
+ * beyond `cap` is written, so a return value > cap means "call again with a larger buffer".  0 = bad arguments. */
+size_t jxb_format_block(char* buf, size_t cap, size_t rows, const char* chrom, const int64_t* pos, const char* snp,
+                        const char* a0, const char* a1, const float* af, const float* miss_rate, const double* res,
+                        int out_cols, int genetic_model);
+
+/* Header line for 3 / 4 / 6 result columns (AssocResultCols::header, src/io/assoc2tsv.rs:45-57); NULL otherwise. */
+const char* jxb_tsv_header(int out_cols);
+
+/* ---- SURVEY 8(f) "next" rows: the two steps in front of the scan ------------------------------------------------
+ * N1  GRM: grm_packed_f32 / grm_packed_f64, method 1 = centred additive (src/stats/grm.rs:204-608, 3053-3623;
+ *     decode_additive_grm_block_f32, src/decode/decode.rs:728-900).  K = Z Z^T / sum_s 2p(1-p), z = code LUT
+ *     {0-mu, 0 (missing), 1-mu, 2-mu}, mu = 2*clamp(row_maf,0,1).  The contraction runs as exact int8 digit-plane
+ *     MMAs (mu on a 2^-21 grid; csrc/grm.cu), so K does not depend on the batch split or the summation order. */
+typedef struct jxb_grm jxb_grm; /* opaque: the n x n accumulator resident in HBM + batch workspace */
+/* sample_idx_host: nullable (all n_full samples, FAM order); otherwise n_sel positions into the packed rows. */
+int jxb_grm_create(int device, size_t n_full, const int64_t* sample_idx_host, size_t n_sel, int method, jxb_grm** out);
+/* Add `rows` packed SNP rows ([rows][bps], bps = ceil(n_full/4)).  row_maf_host f32[rows] is the prepared allele
+ * frequency the reference takes; NULL => computed on the device over the selected samples (A3 formula).  Every
+ * supplied row enters the GRM unless `qc` says otherwise.  May be called repeatedly; rows are batched internally. */
+int jxb_grm_update(jxb_grm* g, const uint8_t* packed_host, size_t bps, size_t rows, const float* row_maf_host,
+                   const jxb_qc_cfg* qc /* nullable; only with row_maf_host == NULL: rows failing the A3 thresholds
+                                           (src/stats/lmm.rs:1262-1323) are left out */);
+size_t jxb_grm_rows_used(jxb_grm* g);      /* SNP rows that entered the GRM so far */
+/* Scale by 1/sum 2p(1-p) and mirror (grm_scale_and_symmetrize_raw_f64, grm.rs:2771-2786).  k_host f64[n,n]
+ * nullable (leave the matrix on the device for jxb_eigh_dev); varsum_out nullable. */
+int jxb_grm_finish(jxb_grm* g, double* k_host, double* varsum_out);
+double* jxb_grm_device_matrix(jxb_grm* g); /* f64[n,n] on the handle's device; valid until jxb_grm_destroy */
+void* jxb_grm_stream(jxb_grm* g);          /* the cudaStream_t the handle's work is ordered on */
+void jxb_grm_destroy(jxb_grm* g);
+
+/* N2  eigendecomposition: rust_eigh_from_array_f64[_inplace] (src/math/eigh.rs:1621-1705, 1883-1990).  One
+ *     cuSOLVER call (cusolverDnXsyevd, dlopen).  a f64[n,n] symmetric; diag_shift is added to the diagonal first (the
+ *     reference's 1e-6 ridge, workflow_model_stream.py:902).  Eigenvalues ascending; the matrix is returned as U^T
+ *     row-major (row k = k-th eigenvector = numpy.linalg.eigh(a)[1].T).  ut_f32_* receive the f32-rounded U^T the
+ *     scan consumes (jxb_model_create[_dev]). */
+int jxb_eigh(int device, size_t n, const double* a_host, double diag_shift, double* evals_host,
+             double* ut_host /* nullable */, float* ut_f32_host /* nullable */);
+/* In place on the device: a_dev is overwritten by U^T.  Synchronises `stream` once (convergence flag); the
+ * ut_f32_dev conversion is enqueued on `stream` after that. */
+int jxb_eigh_dev(int device, size_t n, double* a_dev, double diag_shift, double* evals_dev,
+                 float* ut_f32_dev /* nullable */, void* stream);
+/* N1 -> N2 chained on the device (the f64 matrix never visits the host): jxb_grm_finish, then K + diag_shift*I is
+ * decomposed in place (the handle's matrix becomes U^T; no further updates).  evals_host f64[n], ut_f32_host f32[n,n]. */
+int jxb_grm_eigh(jxb_grm* g, double diag_shift, double* evals_host, float* ut_f32_host);
+
 #ifdef __cplusplus
 }
 #endif

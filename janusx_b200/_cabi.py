@@ -85,6 +85,19 @@ SYMBOLS = {
     "jxb_scan_bed_to_tsv": (C.c_int, [_vp, C.POINTER(BedScanCfg), _psz, PROGRESS_CB, _vp]),
     "jxb_format_row": (C.c_size_t, [C.c_char_p, C.c_size_t, C.c_char_p, C.c_int64, C.c_char_p, C.c_char_p,
                                     C.c_char_p, C.c_float, C.c_float, _pd, C.c_int]),
+    "jxb_format_block": (C.c_size_t, [_vp, C.c_size_t, C.c_size_t, C.c_char_p, _vp, C.c_char_p, C.c_char_p, C.c_char_p,
+                                      _vp, _vp, _vp, C.c_int, C.c_int]),
+    "jxb_tsv_header": (C.c_char_p, [C.c_int]),
+    "jxb_grm_create": (C.c_int, [C.c_int, C.c_size_t, _vp, C.c_size_t, C.c_int, C.POINTER(_vp)]),
+    "jxb_grm_update": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, _vp, C.POINTER(QcCfg)]),
+    "jxb_grm_rows_used": (C.c_size_t, [_vp]),
+    "jxb_grm_finish": (C.c_int, [_vp, _vp, _pd]),
+    "jxb_grm_device_matrix": (_vp, [_vp]),
+    "jxb_grm_stream": (_vp, [_vp]),
+    "jxb_grm_destroy": (None, [_vp]),
+    "jxb_grm_eigh": (C.c_int, [_vp, C.c_double, _vp, _vp]),
+    "jxb_eigh": (C.c_int, [C.c_int, C.c_size_t, _vp, C.c_double, _vp, _vp, _vp]),
+    "jxb_eigh_dev": (C.c_int, [C.c_int, C.c_size_t, _vp, C.c_double, _vp, _vp, _vp]),
 }
 
 

@@ -175,13 +175,15 @@ class FvLMM(LMM):
 
 
 def _eigh(k: np.ndarray, device: int = 0):
-    """Null-model eigendecomposition: a cuSOLVER library call through torch (LAPACK dsyevd in
-    the reference, src/math/eigh.rs:1320; 'library call on GPU, not a hand kernel').  Ascending eigenvalues,
-    eigenvectors in columns."""
-    import torch
+    """Null-model eigendecomposition through the library's own entry point (jxb_eigh: one cuSOLVER Xsyevd call;
+    SURVEY 8a A17: LAPACK dsyevd in the reference, src/math/eigh.rs:1320 -- 'library call on GPU, not a hand
+    kernel').  Ascending eigenvalues, eigenvectors in columns."""
+    from ._cabi import check, lib, ptr, require_gpu
 
-    if not torch.cuda.is_available():
-        raise jxrs.JxbError("no CUDA device is visible: janusx_b200 has no CPU fallback")
-    kt = torch.as_tensor(k, dtype=torch.float64, device=f"cuda:{device}")
-    w, v = torch.linalg.eigh(kt)
-    return w.cpu().numpy(), v.cpu().numpy()
+    require_gpu()
+    k = np.ascontiguousarray(k, dtype=np.float64)
+    n = k.shape[0]
+    w = np.empty(n, dtype=np.float64)
+    ut = np.empty((n, n), dtype=np.float64)
+    check(lib().jxb_eigh(int(device), n, ptr(k), 0.0, ptr(w), ptr(ut), None))
+    return w, ut.T

@@ -213,9 +213,9 @@ const char* header_for(int out_cols) {
 
 }  // namespace
 
-extern "C" size_t jxb_format_row(char* buf, size_t cap, const char* chrom, int64_t pos, const char* snp,
-                                 const char* a0, const char* a1, float af, float miss_rate, const double* row,
-                                 int out_cols) {
+static size_t format_row_impl(char* buf, size_t cap, const char* chrom, int64_t pos, const char* snp,
+                              const char* a0, const char* a1, float af, float miss_rate, const double* row,
+                              int out_cols, bool resolve_name) {
     const double beta = row[0], se = row[1];
     const bool valid = std::isfinite(beta) && std::isfinite(se) && se > 0.0;
     // sanitize_assoc_pvalue, src/math/linalg.rs:99-108
@@ -233,7 +233,7 @@ extern "C" size_t jxb_format_row(char* buf, size_t cap, const char* chrom, int64
     auto tab = [&]() { if (w < end - 1) *w++ = '\t'; };
     put_s(chrom); tab();
     w += snprintf(w, (size_t)(end - w), "%lld", (long long)pos); tab();
-    if (snp[0] == '\0' || (snp[0] == '.' && snp[1] == '\0')) {
+    if (resolve_name && (snp[0] == '\0' || (snp[0] == '.' && snp[1] == '\0'))) {
         w += snprintf(w, (size_t)(end - w), "%s_%lld", chrom, (long long)pos);
     } else {
         put_s(snp);
@@ -257,6 +257,48 @@ extern "C" size_t jxb_format_row(char* buf, size_t cap, const char* chrom, int64
     if (w < end - 1) *w++ = '\n';
     *w = '\0';
     return (size_t)(w - buf);
+}
+
+extern "C" size_t jxb_format_row(char* buf, size_t cap, const char* chrom, int64_t pos, const char* snp,
+                                 const char* a0, const char* a1, float af, float miss_rate, const double* row,
+                                 int out_cols) {
+    return format_row_impl(buf, cap, chrom, pos, snp, a0, a1, af, miss_rate, row, out_cols, true);
+}
+
+// transform_alleles_by_model, src/io/assoc2tsv.rs:117-137
+static void alleles_by_model(const char* r, const char* a, int gm, std::string& a0, std::string& a1) {
+    const std::string R(r), A(a);
+    switch (gm) {
+        case 1: a0 = R + R; a1 = R + A + "/" + A + A; break;           // dom
+        case 2: a0 = R + A + "/" + R + R; a1 = A + A; break;           // rec
+        case 3: a0 = R + R + "/" + A + A; a1 = R + A; break;           // het
+        default: a0 = R; a1 = A; break;
+    }
+}
+
+extern "C" size_t jxb_format_block(char* buf, size_t cap, size_t rows, const char* chrom, const int64_t* pos,
+                                   const char* snp, const char* a0, const char* a1, const float* af,
+                                   const float* miss_rate, const double* res, int out_cols, int genetic_model) {
+    if (!(out_cols == 3 || out_cols == 4 || out_cols == 6) || genetic_model < 0 || genetic_model > 3) return 0;
+    size_t used = 0;
+    std::string t0, t1;
+    std::vector<char> line;
+    for (size_t r = 0; r < rows; ++r) {
+        alleles_by_model(a0, a1, genetic_model, t0, t1);
+        const size_t need = strlen(chrom) * 2 + strlen(snp) + t0.size() + t1.size() + 512;
+        if (line.size() < need) line.resize(need);
+        // write_chunk prints the caller's SNP names verbatim (no chrom_pos substitution)
+        const size_t len = format_row_impl(line.data(), line.size(), chrom, pos[r], snp, t0.c_str(), t1.c_str(), af[r],
+                                           miss_rate[r], res + r * (size_t)out_cols, out_cols, false);
+        if (used + len <= cap) memcpy(buf + used, line.data(), len);
+        used += len;
+        chrom += strlen(chrom) + 1; snp += strlen(snp) + 1; a0 += strlen(a0) + 1; a1 += strlen(a1) + 1;
+    }
+    return used;
+}
+
+extern "C" const char* jxb_tsv_header(int out_cols) {
+    return (out_cols == 3 || out_cols == 4 || out_cols == 6) ? header_for(out_cols) : nullptr;
 }
 
 extern "C" int jxb_scan_bed_to_tsv(jxb_model* m, const jxb_bed_scan_cfg* cfg, size_t* rows_written,

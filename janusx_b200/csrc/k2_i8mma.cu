@@ -18,83 +18,22 @@
 #include <cstdlib>
 
 #include "jxb_common.cuh"
+#include "tc05.cuh"
 
 namespace jxb {
 
 namespace {
 
+using namespace tc05;
+
 constexpr int TM = 128;
 constexpr int MSUB = 2;
-constexpr int KSLAB = 128;                       // bytes of K per stage row
 constexpr int STAGES = 3;
 constexpr int A_STAGE = MSUB * TM * KSLAB;       // 32 KB
 constexpr int NTHREADS = 192;
 constexpr int GROUP_M = 16;
 constexpr int ACC_COLS = 256;                    // TMEM column stride between the two accumulators
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-        ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
-        : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// D[tmem] (+)= A[smem desc] x B[smem desc], int8 x int8 -> int32
-__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                          uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u)
-        : "memory");
-}
-__device__ __forceinline__ void tc_ld8(uint32_t taddr, int32_t (&v)[8]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                 : "r"(taddr));
-}
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major SWIZZLE_128B operand: 128-byte rows, 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-    uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFFu);
-    d |= (uint64_t)1 << 16;                 // leading byte offset (unused for swizzled K-major) = 1
-    d |= (uint64_t)(1024 >> 4) << 32;       // stride byte offset between 8-row groups
-    d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
-    return d;
-}
-// cute::UMMA::InstrDescriptor: S32 accumulate, int8 x int8, both K-major
-__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
-    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
 
 __device__ __forceinline__ void tile_coords(int tile, int mt_count, int nt_count, int& mt, int& nt) {
     const int per_group = GROUP_M * nt_count;
@@ -285,35 +224,6 @@ i8_rotate_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)p;
-    }
-    return fn;
-}
-
-// 3-D byte tensor [planes][rows][ld8] with a {128 B, box_rows, box_planes} box, SWIZZLE_128B
-int encode_planes(CUtensorMap* tm, void* base, size_t ld8, size_t rows, size_t planes, int box_rows, int box_planes) {
-    EncodeTiledFn fn = encode_fn();
-    if (!fn) return fail(-101, "cuTensorMapEncodeTiled is unavailable from the CUDA driver");
-    cuuint64_t dims[3] = {(cuuint64_t)ld8, (cuuint64_t)rows, (cuuint64_t)planes};
-    cuuint64_t strides[2] = {(cuuint64_t)ld8, (cuuint64_t)ld8 * rows};
-    cuuint32_t box[3] = {(cuuint32_t)KSLAB, (cuuint32_t)box_rows, (cuuint32_t)box_planes};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(-102, "cuTensorMapEncodeTiled(int8 planes) failed with code " + std::to_string((int)r));
-    return 0;
-}
 
 template <int NSL, int CG>
 int launch_pass(Model& m, const CUtensorMap& tm_a, const CUtensorMap& tm_b, int a_plane, int slice0, int mode,

@@ -8,8 +8,8 @@ FarmCPU, plots, run history, -mem budgeting, LM switch) is out of scope; unsuppo
 
   python -m janusx_b200.gwas -bfile panel -p pheno.tsv -n 0 -lmm -k 1 -q 3 -o out -prefix run1
 
-The GRM (-k 1) and its eigendecomposition are input preparation done with torch on the GPU (cuBLAS / cuSOLVER
-library calls; SURVEY 8f rows N1/N2 are "next").
+The GRM (-k 1) is built on the device by the int8 tensor-core kernel (csrc/grm.cu) and decomposed
+by the library's cuSOLVER entry point (csrc/eigh.cu, row N2); no torch is involved.
 """
 from __future__ import annotations
 
@@ -69,29 +69,25 @@ def _read_fam(prefix: str) -> List[str]:
         return [line.split()[1] for line in fh if line.strip()]
 
 
-def _grm_from_bed(prefix: str, n_full: int, device: int) -> np.ndarray:
-    """Centred VanRaden GRM (src/stats/grm.rs:343-356) with torch on the GPU (input preparation)."""
-    import torch
-    dev = torch.device(f"cuda:{device}")
-    raw = np.fromfile(prefix + ".bed", dtype=np.uint8)
+def _grm_from_bed(prefix: str, n_full: int, device: int, maf: float, geno: float, het: float) -> np.ndarray:
+    """Centred VanRaden GRM (src/stats/grm.rs:204-608) over the SNPs passing the scan's QC thresholds, accumulated on
+    the device by the int8 tensor-core kernel (csrc/grm.cu) from the memory-mapped BED."""
+    from . import jxrs
     bps = (n_full + 3) // 4
-    packed = torch.as_tensor(raw[3:].reshape(-1, bps), device=dev)
-    K = torch.zeros((n_full, n_full), dtype=torch.float64, device=dev)
-    denom = 0.0
-    lut = torch.tensor([0.0, float("nan"), 1.0, 2.0], dtype=torch.float64, device=dev)
-    sh = torch.tensor([0, 2, 4, 6], dtype=torch.uint8, device=dev)
-    for r0 in range(0, packed.shape[0], 8192):
-        blk = packed[r0:r0 + 8192]
-        codes = ((blk[:, :, None] >> sh[None, None, :]) & 3).reshape(blk.shape[0], -1)[:, :n_full]
-        g = lut[codes.long()]
-        mu = torch.nanmean(g, dim=1, keepdim=True)
-        g = torch.where(torch.isnan(g), mu, g)
-        pfreq = mu[:, 0] / 2.0
-        keep = (pfreq > 0) & (pfreq < 1)
-        z = (g - mu)[keep]
-        denom += float((2.0 * pfreq[keep] * (1.0 - pfreq[keep])).sum())
-        K += z.T @ z
-    return (K / max(denom, 1e-12)).cpu().numpy()
+    raw = np.memmap(prefix + ".bed", dtype=np.uint8, mode="r")
+    if raw.shape[0] < 3 or bytes(raw[:3]) != b"\x6c\x1b\x01":
+        raise SystemExit(f"{prefix}.bed: not a SNP-major PLINK BED file")
+    packed = raw[3:3 + (raw.shape[0] - 3) // bps * bps].reshape(-1, bps)
+    g = jxrs.DeviceGrm(n_full, None, 1, device)
+    try:
+        for r0 in range(0, packed.shape[0], 65536):
+            g.update(np.ascontiguousarray(packed[r0:r0 + 65536]), None, qc=(maf, geno, het))
+        if g.rows_used == 0:
+            raise SystemExit("no SNP passed the QC thresholds: cannot build the GRM")
+        k, _ = g.finish()
+    finally:
+        g.close()
+    return k
 
 
 def main(argv: Optional[List[str]] = None) -> int:
@@ -107,7 +103,7 @@ def main(argv: Optional[List[str]] = None) -> int:
     outprefix = os.path.join(args.out, prefix)
 
     if args.grm == "1":
-        K_full = _grm_from_bed(args.bfile, len(fam), args.gpu)
+        K_full = _grm_from_bed(args.bfile, len(fam), args.gpu, args.maf, args.geno, args.het)
     elif args.grm.endswith(".npy"):
         K_full = np.load(args.grm)
     else:

@@ -592,6 +592,451 @@ def fvlmm_assoc_bed_to_tsv_f32(bed_prefix, out_tsv, s, xcov, y_rot, log10_lbd, u
     return rows, pve, float(meta["log_det_v"])
 
 
+# ------------------------------------------------------------------------------------------------------
+# TSV writer + packed-array scans (route "B" callers that already hold packed rows / result blocks)
+# ------------------------------------------------------------------------------------------------------
+def _blob(strings) -> bytes:
+    return b"\0".join(str(x).encode() for x in strings) + b"\0"
+
+
+def _format_block(chrom, pos, snp, a0, a1, af, miss_rate, results, genetic_model="add") -> bytes:
+    res = _f64(results)
+    rows, cols = res.shape
+    if rows == 0:
+        return b""
+    pos = np.ascontiguousarray(pos, dtype=np.int64)
+    af = np.ascontiguousarray(af, dtype=np.float32)
+    mr = np.ascontiguousarray(miss_rate, dtype=np.float32)
+    blobs = [_blob(v) for v in (chrom, snp, a0, a1)]
+    cap = 160 * rows + sum(len(b) for b in blobs) * 3
+    for _ in range(2):
+        buf = C.create_string_buffer(cap)
+        need = lib().jxb_format_block(buf, cap, rows, blobs[0], ptr(pos), blobs[1], blobs[2], blobs[3], ptr(af), ptr(mr),
+                                      ptr(res), cols, _model_code(genetic_model))
+        if need == 0:
+            raise ValueError(f"results must have 3, 4 or 6 columns, got {cols}")
+        if need <= cap:
+            return buf.raw[:need]
+        cap = need
+    raise RuntimeError("TSV block formatting failed")
+
+
+class SiteInfo:
+    """chrom / pos / ref_allele / alt_allele record (PySiteInfo in the reference)."""
+    __slots__ = ("chrom", "pos", "ref_allele", "alt_allele")
+
+    def __init__(self, chrom, pos, ref_allele, alt_allele):
+        self.chrom, self.pos, self.ref_allele, self.alt_allele = str(chrom), int(pos), str(ref_allele), str(alt_allele)
+
+
+class GwasAssocTsvWriter:
+    """src/io/assoc2tsv.rs:765-892: association TSV sink; the header is written when the first block fixes the
+    schema (3 / 4 / 6 result columns); rows are formatted by the library (jxb_format_block)."""
+
+    def __init__(self, path, genetic_model="add"):
+        key = str(genetic_model).strip().lower()
+        if key not in ("add", "dom", "rec", "het"):
+            raise ValueError("genetic_model must be one of: add, dom, rec, het")
+        self._path, self._model, self._cols, self._fh, self._rows, self._closed = str(path), key, None, None, 0, False
+
+    def _ensure(self, cols):
+        if cols not in (3, 4, 6):
+            raise ValueError(f"unsupported results column count: {cols}")
+        if self._closed:
+            raise IOError("writer is closed")
+        if self._cols is None:
+            self._cols = cols
+            self._fh = open(self._path, "wb", buffering=8 << 20)
+            self._fh.write(lib().jxb_tsv_header(cols))
+        elif self._cols != cols:
+            raise ValueError(f"inconsistent results columns across chunks: expected {self._cols}, got {cols}")
+
+    def write_chunk(self, sites, snp, maf, miss, results) -> int:
+        sites = list(sites)
+        if not sites:
+            return 0
+        snp = list(snp)
+        if len(snp) != len(sites):
+            raise ValueError(f"snp length mismatch: snp={len(snp)}, sites={len(sites)}")
+        maf, miss = np.asarray(maf), np.asarray(miss)
+        if maf.shape[0] != len(sites):
+            raise ValueError(f"maf length mismatch: maf={maf.shape[0]}, sites={len(sites)}")
+        if miss.shape[0] != len(sites):
+            raise ValueError(f"miss length mismatch: miss={miss.shape[0]}, sites={len(sites)}")
+        res = np.asarray(results)
+        if res.ndim != 2:
+            raise ValueError("results must be 2D")
+        if res.shape[0] != len(sites):
+            raise ValueError(f"results row mismatch: results={res.shape[0]}, sites={len(sites)}")
+        if res.shape[1] < 3:
+            raise ValueError(f"results must have at least 3 columns, got {res.shape[1]}")
+        self._ensure(res.shape[1])
+        get = (lambda s, k, i: getattr(s, k)) if hasattr(sites[0], "chrom") else (lambda s, k, i: s[i])
+        text = _format_block([get(s, "chrom", 0) for s in sites], [int(get(s, "pos", 1)) for s in sites], snp,
+                             [get(s, "ref_allele", 2) for s in sites], [get(s, "alt_allele", 3) for s in sites],
+                             maf, miss, res, self._model)
+        self._fh.write(text)
+        self._rows += len(sites)
+        return len(sites)
+
+    def append_text(self, text, has_plrt, rows):
+        if rows == 0 or not text:
+            return
+        self._ensure(4 if has_plrt else 3)
+        self._fh.write(text.encode() if isinstance(text, str) else bytes(text))
+        self._rows += int(rows)
+
+    def send_block(self, data):
+        if not data:
+            return
+        if self._fh is None or self._closed:
+            raise IOError("writer is closed")
+        self._fh.write(bytes(data))
+
+    def flush(self):
+        if self._fh is not None and not self._closed:
+            self._fh.flush()
+
+    def close(self):
+        if self._fh is not None and not self._closed:
+            self._fh.close()
+        self._closed = True
+
+    @property
+    def rows_written(self) -> int:
+        return self._rows
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _packed_args(packed, n_samples, row_flip, row_maf, s, xcov, y_rot, u_t, sample_indices, row_indices, low, high, tol):
+    """Validation of src/stats/lmm.rs:3089-3187 (same messages); returns (packed rows to scan, sample index)."""
+    if n_samples == 0:
+        raise RuntimeError("n_samples must be > 0")
+    if low >= high:
+        raise RuntimeError("low must be < high")
+    if not (math.isfinite(tol) and tol > 0.0):
+        raise RuntimeError("tol must be positive and finite")
+    packed = np.asarray(packed)
+    if packed.ndim != 2:
+        raise RuntimeError("packed must be 2D (m, bytes_per_snp)")
+    m_packed, bps = packed.shape
+    if bps != (n_samples + 3) // 4:
+        raise RuntimeError(f"packed second dimension mismatch: got {bps}, expected {(n_samples + 3) // 4}")
+    if row_indices is not None:
+        ridx = np.asarray(row_indices, dtype=np.int64).reshape(-1)
+        if ridx.size and (ridx.min() < 0 or ridx.max() >= m_packed):
+            raise RuntimeError("row_indices out of range")
+        packed = packed[ridx]
+    m = packed.shape[0]
+    if np.asarray(row_flip).shape[0] != m or np.asarray(row_maf).shape[0] != m:
+        raise RuntimeError("row_flip/row_maf length mismatch with packed rows")
+    if np.any(np.asarray(row_flip, dtype=bool)):
+        raise NotImplementedError("row_flip=True is not supported (never set by the reference on this path)")
+    n = np.asarray(y_rot).reshape(-1).shape[0]
+    if n == 0:
+        raise RuntimeError("y_rot must not be empty")
+    sidx = None
+    if sample_indices is not None:
+        sidx = np.asarray(sample_indices, dtype=np.int64).reshape(-1)
+        if sidx.shape[0] != n:
+            raise RuntimeError(f"sample_indices length mismatch: got {sidx.shape[0]}, expected {n}")
+        if sidx.size and (sidx.min() < 0 or sidx.max() >= n_samples):
+            raise RuntimeError("sample_indices out of range")
+    elif n != n_samples:
+        raise RuntimeError(f"len(y_rot)={n} must equal n_samples={n_samples} when sample_indices is not provided")
+    _check_bed_args(s, xcov, y_rot, u_t, low, high, tol)
+    return np.ascontiguousarray(packed, dtype=np.uint8), sidx
+
+
+def _scan_packed_all_rows(mdl, packed, n_samples, sidx, row_maf, model, low, high, max_iter, tol, init, nullml,
+                          progress_callback, progress_every):
+    """Every supplied row is scanned (thresholds off: the caller already filtered).  The device recomputes the
+    allele frequency that drives imputation; a `row_maf` that disagrees means the metadata belongs to other
+    samples, which is refused rather than silently ignored."""
+    m = packed.shape[0]
+    cols = 4 if nullml is not None else 3
+    out = np.zeros((m, cols), dtype=np.float64)
+    af_all = np.zeros(m, dtype=np.float32)
+    miss_all = np.zeros(m, dtype=np.int32)
+    step = DEFAULT_DEVICE_BATCH if not progress_every else max(1, min(int(progress_every), DEFAULT_DEVICE_BATCH))
+    for r0 in range(0, m, step):
+        r1 = min(m, r0 + step)
+        keep, af, missing, res = mdl.scan_packed(packed[r0:r1], n_samples, sidx, None, 0.0, 1.0, 0.0, model, "lmm", low, high,
+                                                 max_iter, tol, init, nullml)
+        if not keep.all():
+            raise RuntimeError("internal error: packed scan dropped rows with QC disabled")
+        out[r0:r1], af_all[r0:r1], miss_all[r0:r1] = res, af, missing
+        if progress_callback is not None:
+            progress_callback(r1, m)
+    want = np.asarray(row_maf, dtype=np.float32)
+    bad = ~((want == af_all) | (np.isnan(want) & np.isnan(af_all)))
+    if bad.any():
+        i = int(np.nonzero(bad)[0][0])
+        raise RuntimeError(f"row_maf[{i}]={want[i]!r} differs from the allele frequency of the packed row over the "
+                           f"selected samples ({af_all[i]!r}); prepared metadata must come from the same samples")
+    return out, miss_all
+
+
+def lmm_reml_assoc_packed_f32(packed, n_samples, row_flip, row_maf, s, xcov, y_rot, u_t, sample_indices=None,
+                              row_indices=None, low=-5.0, high=5.0, max_iter=50, tol=1e-2, threads=0, model="add",
+                              progress_callback=None, progress_every=0, nullml=None, init_log10_lbd=None,
+                              rotate_block_rows=256):
+    """src/stats/lmm.rs:3040-3362 -> f64[m, 3|4].  `init_log10_lbd` seeds every SNP (no carried warm start)."""
+    _model_code(model)
+    packed, sidx = _packed_args(packed, n_samples, row_flip, row_maf, s, xcov, y_rot, u_t, sample_indices, row_indices,
+                                low, high, tol)
+    init = None
+    if init_log10_lbd is not None and math.isfinite(init_log10_lbd):
+        init = min(max(float(init_log10_lbd), low), high)
+    mdl = _get_model(s, xcov, y_rot, u_t)
+    out, _ = _scan_packed_all_rows(mdl, packed, n_samples, sidx, row_maf, model, low, high, max_iter, tol, init, nullml,
+                                   progress_callback, progress_every)
+    return out
+
+
+def _read_bim_columns(prefix, row_indices):
+    chrom, pos, snp, a0, a1 = [], [], [], [], []
+    with open(str(prefix) + ".bim") as fh:
+        for ln, line in enumerate(fh, 1):
+            tok = line.split()
+            if len(tok) < 6:
+                raise RuntimeError(f"Malformed BIM line at {prefix}.bim:{ln}: {line.rstrip()}")
+            chrom.append(tok[0]); snp.append(tok[1]); a0.append(tok[4]); a1.append(tok[5])
+            try:
+                v = int(tok[3])
+                pos.append(v if -(1 << 31) <= v < (1 << 31) else 0)
+            except ValueError:
+                pos.append(0)
+    cols = (chrom, pos, snp, a0, a1)
+    if row_indices is not None:
+        cols = tuple([c[int(i)] for i in row_indices] for c in cols)
+    return cols
+
+
+def lmm_reml_assoc_packed_f32_to_tsv(packed, n_samples, row_flip, row_maf, row_missing, s, xcov, y_rot, u_t, chrom, pos,
+                                     snp, allele0, allele1, out_tsv, sample_indices=None, row_indices=None, low=-5.0,
+                                     high=5.0, max_iter=50, tol=1e-2, threads=0, model="add", progress_callback=None,
+                                     progress_every=0, nullml=None, init_log10_lbd=None, rotate_block_rows=256,
+                                     bed_prefix=None) -> int:
+    """src/stats/lmm.rs:3364-3800 -> rows written.  af column = `row_maf`; miss column = the count recovered from
+    `row_missing` (round(rate * n)) divided by n again, in f32 (lmm.rs:1934-1950, 3704-3707)."""
+    _model_code(model)
+    packed, sidx = _packed_args(packed, n_samples, row_flip, row_maf, s, xcov, y_rot, u_t, sample_indices, row_indices,
+                                low, high, tol)
+    m = packed.shape[0]
+    if np.asarray(row_missing).shape[0] != m:
+        raise RuntimeError("row_flip/row_maf/row_missing length mismatch with packed rows")
+    cols_meta = [list(chrom), list(pos), list(snp), list(allele0), list(allele1)]
+    if all(len(c) == 0 for c in cols_meta):
+        if bed_prefix is None or not str(bed_prefix).strip():
+            raise RuntimeError("empty TSV metadata requires non-empty bed_prefix")
+        cols_meta = list(_read_bim_columns(str(bed_prefix).strip(), row_indices))
+        if any(len(c) != m for c in cols_meta):
+            raise RuntimeError(f"BIM metadata length mismatch: expected={m}")
+    elif any(len(c) != m for c in cols_meta):
+        raise RuntimeError(f"TSV metadata length mismatch: rows={m}, chrom={len(cols_meta[0])}, pos={len(cols_meta[1])}, "
+                           f"snp={len(cols_meta[2])}, allele0={len(cols_meta[3])}, allele1={len(cols_meta[4])}")
+    init = None
+    if init_log10_lbd is not None and math.isfinite(init_log10_lbd):
+        init = min(max(float(init_log10_lbd), low), high)
+    mdl = _get_model(s, xcov, y_rot, u_t)
+    out, _ = _scan_packed_all_rows(mdl, packed, n_samples, sidx, row_maf, model, low, high, max_iter, tol, init, nullml,
+                                   progress_callback, progress_every)
+    n = mdl.n
+    rate = np.asarray(row_missing, dtype=np.float32)
+    cnt = np.where(np.isfinite(rate) & (rate > 0), np.round(rate.astype(np.float64) * n), 0.0)
+    miss_rate = cnt.astype(np.float32) / np.float32(n)
+    text = _format_block(*cols_meta, np.asarray(row_maf, dtype=np.float32), miss_rate, out, "add")
+    with open(out_tsv, "wb") as fh:
+        fh.write(lib().jxb_tsv_header(out.shape[1]))
+        fh.write(text)
+    return m
+
+
+class FvLmmAssocCache:
+    """src/stats/fvlmm.rs:1412-1436: handle of the fixed-lambda precomputation (weights, Cholesky of X'WX, ypy).
+    Here the cached state lives with the device model; the object pins (model, log10 lambda)."""
+
+    def __init__(self, mdl: DeviceModel, log10_lbd: float):
+        self._mdl, self._l10 = mdl, float(log10_lbd)
+        self.n, self.p, self.lbd = mdl.n, mdl.p, 10.0 ** float(log10_lbd)
+
+
+def fvlmm_assoc_prepare_cache_f32(s, xcov, y_rot, log10_lbd) -> FvLmmAssocCache:
+    """src/stats/fvlmm.rs:1807-1846."""
+    y = _f64(y_rot).reshape(-1)
+    xc = _f64(xcov)
+    if xc.ndim != 2 or xc.shape[0] != y.shape[0]:
+        raise RuntimeError("Xcov.n_rows must equal len(y_rot)")
+    if _f64(s).reshape(-1).shape[0] != y.shape[0]:
+        raise RuntimeError("len(S) must equal len(y_rot)")
+    if y.shape[0] <= xc.shape[1] + 1:
+        raise RuntimeError("n must be > p_cov+1")
+    lbd = 10.0 ** float(log10_lbd)
+    if not (math.isfinite(lbd) and lbd > 0.0):
+        raise RuntimeError("invalid log10_lbd")
+    # a private device model: the handle must outlive evictions from the array-argument cache
+    return FvLmmAssocCache(DeviceModel(s, xc, y), log10_lbd)
+
+
+def fvlmm_assoc_chunk_with_cache_f32(cache: FvLmmAssocCache, g_rot_chunk, threads=0, nullml=None):
+    """src/stats/fvlmm.rs:1917-1937."""
+    g = np.asarray(g_rot_chunk)
+    if g.ndim != 2 or g.shape[1] != cache.n:
+        raise RuntimeError("g_rot_chunk must be (m, n)")
+    return cache._mdl.fixed_chunk(g, cache._l10, nullml, rotated=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+# SURVEY 8(f) N1 / N2: GRM and its eigendecomposition on the device
+# ------------------------------------------------------------------------------------------------------
+class DeviceGrm:
+    """Streaming centred-additive GRM accumulator in HBM (csrc/grm.cu; src/stats/grm.rs:204-608)."""
+
+    def __init__(self, n_samples: int, sample_indices=None, method: int = 1, device: int = 0):
+        _cabi.require_gpu()
+        if n_samples == 0:
+            raise RuntimeError("n_samples must be > 0")
+        self._sidx = None if sample_indices is None else np.ascontiguousarray(sample_indices, dtype=np.int64).reshape(-1)
+        self.n_full = int(n_samples)
+        self.n = self.n_full if self._sidx is None else int(self._sidx.shape[0])
+        self.device = int(device)
+        h = C.c_void_p()
+        check(lib().jxb_grm_create(self.device, self.n_full, ptr(self._sidx), 0 if self._sidx is None else self.n,
+                                   int(method), C.byref(h)))
+        self._h = h
+
+    @property
+    def handle(self):
+        if self._h is None:
+            raise RuntimeError("GRM handle is closed")
+        return self._h
+
+    def update(self, packed, row_maf=None, qc=None) -> None:
+        """Add packed SNP rows.  row_maf: the prepared allele frequencies (reference semantics); None => computed on
+        the device, optionally with `qc=(maf_thr, miss_thr, het_thr)` leaving failing rows out."""
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        if packed.ndim != 2:
+            raise RuntimeError("packed must be 2D (m, bytes_per_snp)")
+        maf = None if row_maf is None else np.ascontiguousarray(row_maf, dtype=np.float32).reshape(-1)
+        if maf is not None and maf.shape[0] != packed.shape[0]:
+            raise RuntimeError(f"row_maf length mismatch: got {maf.shape[0]}, expected {packed.shape[0]}")
+        cfg = None if qc is None else QcCfg(float(qc[0]), float(qc[1]), float(qc[2]), 0)
+        check(lib().jxb_grm_update(self.handle, ptr(packed), packed.shape[1], packed.shape[0], ptr(maf),
+                                   C.byref(cfg) if cfg is not None else None))
+
+    @property
+    def rows_used(self) -> int:
+        return int(lib().jxb_grm_rows_used(self.handle))
+
+    def finish(self, to_host: bool = True):
+        """-> (K f64[n, n] or None, varsum)."""
+        k = np.empty((self.n, self.n), dtype=np.float64) if to_host else None
+        vs = C.c_double()
+        check(lib().jxb_grm_finish(self.handle, ptr(k), C.byref(vs)))
+        return k, float(vs.value)
+
+    def eigh(self, diag_shift: float = 1e-6):
+        """Finish, then decompose K + diag_shift*I in place on the device -> (S f64[n], U^T f32[n, n]) on the host.
+        The n x n matrix never visits the host in f64."""
+        w = np.empty(self.n, dtype=np.float64)
+        ut32 = np.empty((self.n, self.n), dtype=np.float32)
+        check(lib().jxb_grm_eigh(self.handle, float(diag_shift), ptr(w), ptr(ut32)))
+        return w, ut32
+
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            lib().jxb_grm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _grm_packed(packed, n_samples, row_flip, row_maf, sample_indices, method, progress_callback, progress_every):
+    if n_samples == 0:
+        raise RuntimeError("n_samples must be > 0")
+    if method not in (1, 2, 3):
+        raise RuntimeError(f"unsupported method={method}; expected 1 (centered additive), 2 (standardized additive), "
+                           "or 3 (centered dominance)")
+    if method != 1:
+        raise NotImplementedError("only method=1 (centred additive, the `-k 1` default) runs on the device in this build")
+    packed = np.asarray(packed)
+    if packed.ndim != 2:
+        raise RuntimeError("packed must be 2D (m, bytes_per_snp)")
+    m, bps = packed.shape
+    if m == 0:
+        raise RuntimeError("packed must contain at least one SNP row")
+    if bps != (n_samples + 3) // 4:
+        raise RuntimeError(f"packed second dimension mismatch: got {bps}, expected {(n_samples + 3) // 4}")
+    if np.asarray(row_flip).shape[0] != m:
+        raise RuntimeError(f"row_flip length mismatch: got {np.asarray(row_flip).shape[0]}, expected {m}")
+    if np.asarray(row_maf).shape[0] != m:
+        raise RuntimeError(f"row_maf length mismatch: got {np.asarray(row_maf).shape[0]}, expected {m}")
+    if np.any(np.asarray(row_flip, dtype=bool)):
+        raise NotImplementedError("row_flip=True is not supported")
+    if sample_indices is not None and np.asarray(sample_indices).size == 0:
+        raise RuntimeError("sample_indices must not be empty")
+    g = DeviceGrm(n_samples, sample_indices, method)
+    try:
+        maf = np.asarray(row_maf, dtype=np.float32)
+        step = 65536 if not progress_every else max(1, int(progress_every))
+        for r0 in range(0, m, step):
+            g.update(packed[r0:r0 + step], maf[r0:r0 + step])
+            if progress_callback is not None:
+                progress_callback(min(m, r0 + step), m)
+        k, _ = g.finish()
+    finally:
+        g.close()
+    return k
+
+
+def grm_packed_f64(packed, n_samples, row_flip, row_maf, sample_indices=None, method=1, block_cols=65536, threads=0,
+                   progress_callback=None, progress_every=0):
+    """src/stats/grm.rs:3583-3623 -> f64[n, n]."""
+    return _grm_packed(packed, n_samples, row_flip, row_maf, sample_indices, method, progress_callback, progress_every)
+
+
+def grm_packed_f32(packed, n_samples, row_flip, row_maf, sample_indices=None, method=1, block_cols=65536, threads=0,
+                   progress_callback=None, progress_every=0):
+    """src/stats/grm.rs:3053-3581 -> f32[n, n] (the f64 accumulator cast once, grm.rs:484)."""
+    return _grm_packed(packed, n_samples, row_flip, row_maf, sample_indices, method, progress_callback,
+                       progress_every).astype(np.float32)
+
+
+def rust_eigh_from_array_f64(a, threads=0, driver=None, jobz="V", require_lapack=False):
+    """src/math/eigh.rs:1621-1705 -> (evals, evecs | None, backend, evd_backend, n, threads_before, threads_in_stage,
+    threads_after, lapack_used, elapsed_s).  Eigenvalues ascending, eigenvectors in columns (numpy convention)."""
+    import time
+    a = np.asarray(a)
+    if a.ndim != 2 or a.shape[0] == 0 or a.shape[0] != a.shape[1]:
+        shape = tuple(a.shape) + (0, 0)
+        raise RuntimeError(f"rust_eigh_from_array_f64 expects a non-empty square matrix; got shape=({shape[0]}, {shape[1]})")
+    if require_lapack:
+        raise RuntimeError("rust_eigh_from_array_f64 expected LAPACK backend, got cusolver_xsyevd")
+    _cabi.require_gpu()
+    a = _f64(a)
+    n = a.shape[0]
+    want_v = str(jobz).strip().upper() != "N"
+    w = np.empty(n, dtype=np.float64)
+    ut = np.empty((n, n), dtype=np.float64) if want_v else None
+    t0 = time.perf_counter()
+    check(lib().jxb_eigh(0, n, ptr(a), 0.0, ptr(w), ptr(ut), None))
+    dt = time.perf_counter() - t0
+    return w, (ut.T if want_v else None), "cuda", "cusolver_xsyevd", n, 0, 0, 0, False, dt
+
+
+rust_eigh_from_array_f64_inplace = rust_eigh_from_array_f64
+
+
 def gwas_lmm_lm_null_lrt_decision(y, x_cov, lmm_ml0, alpha=0.05, boundary_mixture=True):
     """src/stats/gwas_unified.rs:119-175 -> (switch_to_lm, lrt_stat, pval, lm_ml0).
 

@@ -371,6 +371,45 @@ def format_row(chrom: str, pos: int, snp: str, a0: str, a1: str, af: float, miss
 
 
 # ------------------------------------------------------------------------------------------
+# N1: centred additive GRM -- numpy restatement, f64 contraction
+# ------------------------------------------------------------------------------------------
+def grm_packed_f64(packed, n_samples, row_flip, row_maf, sample_indices=None, method=1, mu_grid_bits=None):
+    """src/stats/grm.rs:204-608 with decode_additive_grm_block_f32 (src/decode/decode.rs:803-845, subset path
+    src/math/bedmath.rs:1359-1440): z = LUT[code], LUT = [0-mu, 0 (missing), 1-mu, 2-mu] in f32, mu = 2*clamp(p,0,1);
+    K = Z Z^T / sum_s f64(f32(2p(1-p))), symmetric.  The reference contracts with an f32 SYRK (order-dependent);
+    this restatement contracts in f64.  `mu_grid_bits=b` rounds mu to a 2^-b grid first (the device kernel's
+    arithmetic), in which case z is exact in f64."""
+    assert method == 1, "only the centred additive GRM is restated"
+    packed = np.ascontiguousarray(packed, dtype=np.uint8)
+    m, bps = packed.shape
+    assert bps == (n_samples + 3) // 4
+    assert not np.any(np.asarray(row_flip, dtype=bool))
+    idx = np.arange(n_samples) if sample_indices is None else np.asarray(sample_indices, dtype=np.int64)
+    p = np.clip(np.asarray(row_maf, dtype=np.float32), np.float32(0), np.float32(1))
+    p = np.where(np.isnan(p), np.float32(0), p).astype(np.float32)
+    mean_g = (np.float32(2.0) * p).astype(np.float32)
+    var = (np.float32(2.0) * p * (np.float32(1.0) - p)).astype(np.float32)
+    varsum = float(np.sum(np.where(np.isfinite(var) & (var > 0), var.astype(np.float64), 0.0)))
+    if not (np.isfinite(varsum) and varsum > 0.0):
+        raise RuntimeError("invalid centered GRM denominator: sum(2p(1-p)) <= 0")
+    n = idx.shape[0]
+    K = np.zeros((n, n), dtype=np.float64)
+    for r0 in range(0, m, 4096):
+        blk = packed[r0:r0 + 4096]
+        codes = (blk[:, idx >> 2] >> (2 * (idx & 3)).astype(np.uint8)) & 3
+        mg = mean_g[r0:r0 + 4096]
+        if mu_grid_bits is None:
+            lut = np.stack([np.float32(0) - mg, np.zeros_like(mg), np.float32(1) - mg, np.float32(2) - mg], axis=1)
+            lut = lut.astype(np.float32).astype(np.float64)
+        else:
+            mu = np.rint(mg.astype(np.float64) * 2.0 ** mu_grid_bits) / 2.0 ** mu_grid_bits
+            lut = np.stack([0.0 - mu, np.zeros_like(mu), 1.0 - mu, 2.0 - mu], axis=1)
+        z = np.take_along_axis(lut, codes.astype(np.int64), axis=1)      # [rows, n]
+        K += z.T @ z
+    return K / varsum, varsum
+
+
+# ------------------------------------------------------------------------------------------
 # A1/A15: PLINK readers + the BED -> TSV scan, composed from the pieces above
 # ------------------------------------------------------------------------------------------
 def read_fam(prefix: str):

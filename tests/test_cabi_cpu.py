@@ -70,6 +70,43 @@ def test_format_row_matches_oracle(cabi, oracle):
         assert buf.raw[:n] == oracle.format_row("7", 1000 + i, snp, "A", "TG", float(af), float(mr), a), (i, r)
 
 
+def test_tsv_writer_blocks_match_oracle_rows(cabi, oracle, tmp_path):
+    """GwasAssocTsvWriter (assoc2tsv.rs:765-892): header by schema, verbatim SNP names, allele strings by model."""
+    from janusx_b200 import jxrs
+    rng = np.random.default_rng(1)
+    m = 300
+    sites = [jxrs.SiteInfo(str(1 + i % 5), 100 + i, "ACGT"[i % 4], "TGCA"[i % 4] + ("C" if i % 11 == 0 else "")) for i in range(m)]
+    snp = ["." if i % 7 == 0 else f"rs{i}" for i in range(m)]
+    maf = rng.random(m).astype(np.float32)
+    miss = (rng.random(m) * 0.05).astype(np.float32)
+    for cols, model in ((3, "add"), (4, "dom"), (6, "rec"), (3, "het")):
+        res = rng.normal(size=(m, cols)) * 10.0 ** rng.integers(-6, 6, size=(m, cols))
+        res[:, 1:3] = np.abs(res[:, 1:3])
+        res[5, :2] = np.nan
+        path = tmp_path / f"w{cols}{model}.tsv"
+        w = jxrs.GwasAssocTsvWriter(str(path), model)
+        assert w.write_chunk(sites[:100], snp[:100], maf[:100], miss[:100], res[:100]) == 100
+        assert w.write_chunk(sites[100:], snp[100:], maf[100:], miss[100:], res[100:]) == m - 100
+        with pytest.raises(ValueError, match="inconsistent results columns"):
+            w.write_chunk(sites[:1], snp[:1], maf[:1], miss[:1], np.zeros((1, 4 if cols != 4 else 3)))
+        with pytest.raises(ValueError, match="snp length mismatch"):
+            w.write_chunk(sites[:2], snp[:1], maf[:2], miss[:2], res[:2])
+        w.close()
+        assert w.rows_written == m
+        lines = path.read_bytes().split(b"\n")
+        assert lines[0].split(b"\t")[:7] == [b"chrom", b"pos", b"snp", b"allele0", b"allele1", b"af", b"miss"]
+        assert len(lines[0].split(b"\t")) == 8 + cols and len(lines) == m + 2
+        for i in (0, 5, 7, 11, 123, m - 1):
+            r, a = sites[i].ref_allele, sites[i].alt_allele
+            a0, a1 = {"add": (r, a), "dom": (r + r, r + a + "/" + a + a), "rec": (r + a + "/" + r + r, a + a),
+                      "het": (r + r + "/" + a + a, r + a)}[model]
+            want = oracle.format_row(sites[i].chrom, sites[i].pos, snp[i] if snp[i] != "." else "\x01", a0, a1,
+                                     float(maf[i]), float(miss[i]), res[i]).replace(b"\x01", b".")
+            assert lines[1 + i] + b"\n" == want, (model, i)
+    with pytest.raises(ValueError, match="genetic_model must be one of"):
+        jxrs.GwasAssocTsvWriter(str(tmp_path / "x.tsv"), "mult")
+
+
 def test_argument_validation_messages():
     from janusx_b200 import jxrs
     n = 8

@@ -209,6 +209,69 @@ def test_end_to_end_from_snp_and_packed(jx, oracle):
     assert_results_close(out3, want3)
 
 
+def test_packed_array_entry_points_and_tsv_writer(jx, oracle, tmp_path):
+    """lmm_reml_assoc_packed_f32[_to_tsv] (lmm.rs:3040-3800), GwasAssocTsvWriter, FvLmmAssocCache."""
+    case = make_problem(n=300, m=260, q=2, seed=5, missing_rate=0.02)
+    nm = null_model(oracle, case)
+    n = case.n
+    keep, af, mr, missing = oracle.count_qc_block(case.packed, n, None, 0.02, 0.05, 1.0)
+    idx = np.nonzero(keep)[0]
+    g = oracle.decode_centered_block(case.packed, n, af[idx], row_indices=idx)
+    l10 = float(np.log10(nm["lbd"]))
+    rot = oracle.rotate_block(g, nm["ut"])
+    want = oracle.lmm_reml_chunk_f32(case.s, nm["xcov"], nm["y"], nm["low"], nm["high"], rot, 50, 1e-2,
+                                     nullml=nm["ml0"], init_log10_lbd=l10)
+    flip = np.zeros(idx.size, bool)
+    seen = []
+    got = jx.lmm_reml_assoc_packed_f32(case.packed, n, flip, af[idx], case.s, nm["xcov"], nm["y"], nm["ut"],
+                                       row_indices=idx, low=nm["low"], high=nm["high"], nullml=nm["ml0"],
+                                       init_log10_lbd=l10, progress_callback=lambda d, t: seen.append((d, t)),
+                                       progress_every=100)
+    assert got.shape == (idx.size, 4) and seen[-1] == (idx.size, idx.size) and len(seen) == -(-idx.size // 100)
+    assert_results_close(got, want, cols_p=(2, 3))
+    # already-selected rows, no row_indices: identical
+    got2 = jx.lmm_reml_assoc_packed_f32(case.packed[idx], n, flip, af[idx], case.s, nm["xcov"], nm["y"], nm["ut"],
+                                        low=nm["low"], high=nm["high"], nullml=nm["ml0"], init_log10_lbd=l10)
+    assert np.array_equal(got, got2, equal_nan=True)
+    with pytest.raises(RuntimeError, match="differs from the allele frequency"):
+        jx.lmm_reml_assoc_packed_f32(case.packed[idx], n, flip, af[idx] * np.float32(0.5), case.s, nm["xcov"], nm["y"],
+                                     nm["ut"], low=nm["low"], high=nm["high"])
+    with pytest.raises(RuntimeError, match="packed second dimension mismatch"):
+        jx.lmm_reml_assoc_packed_f32(case.packed[idx][:, :-1], n, flip, af[idx], case.s, nm["xcov"], nm["y"], nm["ut"])
+    # to_tsv: same numbers, reference row format; metadata from arrays or from the BIM
+    from janusx_b200 import synth
+    prefix = str(tmp_path / "pk")
+    synth.write_plink(prefix, case.packed, n)
+    out_tsv = tmp_path / "pk.tsv"
+    rows = jx.lmm_reml_assoc_packed_f32_to_tsv(case.packed, n, flip, af[idx], mr[idx], case.s, nm["xcov"], nm["y"], nm["ut"],
+                                               [], [], [], [], [], str(out_tsv), row_indices=idx, low=nm["low"],
+                                               high=nm["high"], nullml=nm["ml0"], init_log10_lbd=l10, bed_prefix=prefix)
+    assert rows == idx.size
+    bim = oracle.read_bim(prefix)
+    lines = out_tsv.read_bytes().split(b"\n")
+    assert lines[0] == b"chrom\tpos\tsnp\tallele0\tallele1\taf\tmiss\tbeta\tse\tchisq\tpwald\tplrt" and len(lines) == rows + 2
+    for k in (0, 1, rows // 2, rows - 1):
+        chrom, snp_id, pos, a0, a1 = bim[int(idx[k])]
+        rate = np.float32(np.float32(round(float(mr[idx[k]]) * n)) / np.float32(n))
+        assert lines[1 + k] + b"\n" == oracle.format_row(chrom, pos, snp_id, a0, a1, float(af[idx[k]]), float(rate), got[k])
+    # writer class fed with device results
+    w = jx.GwasAssocTsvWriter(str(tmp_path / "w.tsv"))
+    sites = [jx.SiteInfo(bim[int(i)][0], bim[int(i)][2], bim[int(i)][3], bim[int(i)][4]) for i in idx]
+    rate_all = (np.round(mr[idx].astype(np.float64) * n).astype(np.float32) / np.float32(n))
+    w.write_chunk(sites, [bim[int(i)][1] for i in idx], af[idx], rate_all, got)
+    w.close()
+    assert (tmp_path / "w.tsv").read_bytes() == out_tsv.read_bytes()
+    # fixed-lambda cache handle
+    cache = jx.fvlmm_assoc_prepare_cache_f32(case.s, nm["xcov"], nm["y"], l10)
+    assert (cache.n, cache.p) == (n, nm["xcov"].shape[1]) and abs(cache.lbd - nm["lbd"]) <= 1e-12 * nm["lbd"]
+    want_f = oracle.lmm_assoc_chunk_f32(case.s, nm["xcov"], nm["y"], l10, rot, nullml=nm["ml0"])
+    want_f = want_f[0] if isinstance(want_f, tuple) else want_f
+    got_f = jx.fvlmm_assoc_chunk_with_cache_f32(cache, rot, nullml=nm["ml0"])
+    assert_results_close(got_f, want_f, cols_p=(2, 3))
+    with pytest.raises(RuntimeError, match="g_rot_chunk must be"):
+        jx.fvlmm_assoc_chunk_with_cache_f32(cache, rot[:, :-1])
+
+
 def test_sample_subset_scan(jx, oracle):
     case = make_problem(n=300, m=120, q=2, seed=91, missing_rate=0.03)
     sidx = np.array(sorted(np.random.default_rng(1).choice(300, size=211, replace=False)), dtype=np.int64)
