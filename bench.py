@@ -76,32 +76,40 @@ def gen_packed_batch(torch, n, rows, batch_index, device, want_dosage=False):
     return packed, (torch.cat(dos_all) if want_dosage else None)
 
 
-def build_null_model(torch, n, grm_snps, q, device):
-    """GRM (centred VanRaden, src/stats/grm.rs:343-356) from `grm_snps` synthetic SNPs, + 1e-6 I, eigh in f64
-    (cuSOLVER through torch: a library call), phenotype 100 + G beta + e at pve 0.5, q N(0,1)
-    covariates.  Returns host arrays (s, u_t f32 device tensor, X design, y)."""
-    K = torch.zeros((n, n), dtype=torch.float64, device=device)
-    denom = 0.0
+def build_null_model(torch, n, grm_snps, q, device, timings):
+    """Null-model inputs through the library's own front steps: centred VanRaden GRM of `grm_snps` synthetic SNPs on
+    the int8 tensor cores (csrc/grm.cu; src/stats/grm.rs:204-608), K + 1e-6 I decomposed in place by cuSOLVER
+    (csrc/eigh.cu; workflow_model_stream.py:902).  Phenotype 100 + G beta + e at pve 0.5, q N(0,1)
+    covariates.  Returns host arrays (s, X design, y) and U^T as an f32 device tensor (pyBLUP/assoc.py:1818)."""
+    from janusx_b200 import jxrs
+    grm = jxrs.DeviceGrm(n, None, 1, device.index or 0)
     gv = torch.zeros(n, dtype=torch.float64, device=device)
     gt = torch.Generator(device=device)
     gt.manual_seed(SEED + 1)
-    chunk = 8192
+    chunk = 16384
+    t_grm = 0.0
     for b, r0 in enumerate(range(0, grm_snps, chunk)):
         rows = min(chunk, grm_snps - r0)
-        _, dos = gen_packed_batch(torch, n, rows, 10_000_000 + b, device, want_dosage=True)
-        z = dos.to(torch.float64)
-        mu = z.mean(dim=1, keepdim=True)
-        p = mu[:, 0] / 2.0
-        denom += float((2.0 * p * (1.0 - p)).sum())
-        z -= mu
-        K += z.T @ z
+        packed, dos = gen_packed_batch(torch, n, rows, 10_000_000 + b, device, want_dosage=True)
+        torch.cuda.synchronize(device)
+        t0 = time.perf_counter()
+        grm.update_dev(packed.data_ptr(), rows, packed.shape[1])
+        t_grm += time.perf_counter() - t0
         beta = torch.randn(rows, generator=gt, device=device, dtype=torch.float64)
-        gv += beta @ z
-        del z, dos
-    K /= max(denom, 1e-12)
-    K.diagonal().add_(1e-6)                                   # workflow_model_stream.py:902
-    s, u = torch.linalg.eigh(K)
-    del K
+        for c0 in range(0, rows, 4096):
+            z = dos[c0:c0 + 4096].to(torch.float64)
+            z -= z.mean(dim=1, keepdim=True)
+            gv += beta[c0:c0 + 4096] @ z
+        del z, dos, packed
+    s = torch.empty(n, dtype=torch.float64, device=device)
+    u_t = torch.empty((n, n), dtype=torch.float32, device=device)
+    torch.cuda.synchronize(device)
+    t0 = time.perf_counter()
+    grm.eigh_dev(s.data_ptr(), u_t.data_ptr(), 1e-6)
+    timings["eigh_s"] = time.perf_counter() - t0
+    timings["grm_s"] = t_grm
+    timings["grm_snps"] = grm_snps
+    grm.close()
     vg = float(gv.var(unbiased=False))
     ve = vg  # pve 0.5
     y = 100.0 + gv + torch.randn(n, generator=gt, device=device, dtype=torch.float64) * (ve ** 0.5)
@@ -109,8 +117,6 @@ def build_null_model(torch, n, grm_snps, q, device):
     gc.manual_seed(SEED + 2)
     cov = torch.randn((n, q), generator=gc, device=device, dtype=torch.float64)
     X = torch.cat([torch.ones((n, 1), dtype=torch.float64, device=device), cov], dim=1)
-    u_t = u.T.contiguous().to(torch.float32)                  # pyBLUP/assoc.py:1818
-    del u
     return s.cpu().numpy(), u_t, X.cpu().numpy(), y.cpu().numpy()
 
 
@@ -234,6 +240,7 @@ def main():
 
     # ---- null model: eigh once on rank 0, NCCL broadcast of U^T (f32), S, X_rot, y_rot ----------------
     t_setup = time.time()
+    setup_timings = {}
     if args.impl == "reference" and not have_gpu:
         # CPU-only host: small orthogonal basis from numpy (the reference arm still times the same algorithm)
         rng = np.random.default_rng(SEED)
@@ -249,7 +256,7 @@ def main():
         u_t_dev = None
     else:
         if rank == 0:
-            s_np, u_t_dev, X_np, y_np = build_null_model(torch, n, args.grm_snps, q, device)
+            s_np, u_t_dev, X_np, y_np = build_null_model(torch, n, args.grm_snps, q, device, setup_timings)
         else:
             s_np = np.zeros(n); X_np = np.zeros((n, p)); y_np = np.zeros(n)
             u_t_dev = torch.empty((n, n), dtype=torch.float32, device=device)
@@ -396,7 +403,9 @@ def main():
             "stage_ms_last_step": st,
             "solve": {"mean_objective_evals_per_snp": mean_evals},
             "decode": {"hbm_gb_per_s": ((B * bps + kept * n * (8 if args.rotate_variant == 0 else 3)) / (st["decode"] * 1e-3) / 1e9) if st["decode"] > 0 else None},
-            "null_model": {"lambda": lbd, "ml0": ml0, "reml0": reml0, "setup_s": setup_s},
+            "null_model": dict({"lambda": lbd, "ml0": ml0, "reml0": reml0, "setup_s": setup_s,
+                                "front": "GRM: csrc/grm.cu (tcgen05 int8), eigh: csrc/eigh.cu (cuSOLVER Xsyevd)"},
+                               **setup_timings),
             "kept_snps_per_step": kept, "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:

@@ -208,6 +208,10 @@ int jxb_grm_create(int device, size_t n_full, const int64_t* sample_idx_host, si
 int jxb_grm_update(jxb_grm* g, const uint8_t* packed_host, size_t bps, size_t rows, const float* row_maf_host,
                    const jxb_qc_cfg* qc /* nullable; only with row_maf_host == NULL: rows failing the A3 thresholds
                                            (src/stats/lmm.rs:1262-1323) are left out */);
+/* Same with device-resident inputs on the handle's device (the caller orders its own producer before the call;
+ * the call synchronises the handle's stream before returning). */
+int jxb_grm_update_dev(jxb_grm* g, const uint8_t* packed_dev, size_t bps, size_t rows, const float* row_maf_dev,
+                       const jxb_qc_cfg* qc);
 size_t jxb_grm_rows_used(jxb_grm* g);      /* SNP rows that entered the GRM so far */
 /* Scale by 1/sum 2p(1-p) and mirror (grm_scale_and_symmetrize_raw_f64, grm.rs:2771-2786).  k_host f64[n,n]
  * nullable (leave the matrix on the device for jxb_eigh_dev); varsum_out nullable. */

@@ -90,6 +90,7 @@ SYMBOLS = {
     "jxb_tsv_header": (C.c_char_p, [C.c_int]),
     "jxb_grm_create": (C.c_int, [C.c_int, C.c_size_t, _vp, C.c_size_t, C.c_int, C.POINTER(_vp)]),
     "jxb_grm_update": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, _vp, C.POINTER(QcCfg)]),
+    "jxb_grm_update_dev": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, _vp, C.POINTER(QcCfg)]),
     "jxb_grm_rows_used": (C.c_size_t, [_vp]),
     "jxb_grm_finish": (C.c_int, [_vp, _vp, _pd]),
     "jxb_grm_device_matrix": (_vp, [_vp]),

@@ -359,7 +359,7 @@ int ensure_batch(GrmHandle& g, size_t rows, size_t bps) {
         JXB_CUDA_OK(cudaMalloc((void**)&g.miss, rows * sizeof(float)));
         g.rows_cap = rows;
     }
-    if (rows * bps > g.packed_cap) {
+    if (bps && rows * bps > g.packed_cap) {
         if (g.packed) cudaFree(g.packed);
         g.packed = nullptr;
         JXB_CUDA_OK(cudaMalloc((void**)&g.packed, rows * bps));
@@ -475,42 +475,45 @@ extern "C" void jxb_grm_destroy(jxb_grm* h) {
     delete g;
 }
 
-extern "C" int jxb_grm_update(jxb_grm* h, const uint8_t* packed_host, size_t bps, size_t rows,
-                              const float* row_maf_host, const jxb_qc_cfg* qc) {
-    GrmHandle* g = (GrmHandle*)h;
-    if (!g || (!packed_host && rows)) return fail(-2, "null argument");
+static int grm_update_impl(GrmHandle* g, const uint8_t* packed, bool on_device, size_t bps, size_t rows,
+                           const float* row_maf, const jxb_qc_cfg* qc) {
+    if (!g || (!packed && rows)) return fail(-2, "null argument");
     if (g->finished) return fail(-2, "GRM already finished");
     if (bps != (g->n_full + 3) / 4)
         return fail(-2, "packed second dimension mismatch: got " + std::to_string(bps) + ", expected " +
                             std::to_string((g->n_full + 3) / 4));
     JXB_CUDA_OK(cudaSetDevice(g->device));
-    if (row_maf_host && qc) return fail(-2, "QC thresholds apply only when the allele frequency is computed on the device");
+    if (row_maf && qc) return fail(-2, "QC thresholds apply only when the allele frequency is computed on the device");
+    const cudaMemcpyKind to_dev = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     std::vector<float> af_host;
     std::vector<int32_t> counts_host;
     for (size_t r0 = 0; r0 < rows; r0 += jxb::MAX_BATCH) {
         const size_t cur = std::min(jxb::MAX_BATCH, rows - r0);
-        int rc = jxb::ensure_batch(*g, cur, bps);
+        int rc = jxb::ensure_batch(*g, cur, on_device ? 0 : bps);
         if (rc) return rc;
-        JXB_CUDA_OK(cudaMemcpyAsync(g->packed, packed_host + r0 * bps, cur * bps, cudaMemcpyHostToDevice, g->st));
+        const uint8_t* pk = packed + r0 * bps;
+        if (!on_device) {
+            JXB_CUDA_OK(cudaMemcpyAsync(g->packed, pk, cur * bps, cudaMemcpyHostToDevice, g->st));
+            pk = g->packed;
+        }
         af_host.resize(cur);
-        if (row_maf_host) {
-            JXB_CUDA_OK(cudaMemcpyAsync(g->af, row_maf_host + r0, cur * sizeof(float), cudaMemcpyHostToDevice, g->st));
-            std::copy(row_maf_host + r0, row_maf_host + r0 + cur, af_host.begin());
+        if (row_maf) {
+            JXB_CUDA_OK(cudaMemcpyAsync(g->af, row_maf + r0, cur * sizeof(float), to_dev, g->st));
         } else {
-            // allele frequency over the selected samples, the A3 formula (src/stats/lmm.rs:1262-1323), thresholds off
+            // allele frequency over the selected samples, the A3 formula (src/stats/lmm.rs:1262-1323)
             jxb::Model dummy;
-            rc = jxb::launch_count_qc(dummy, g->packed, bps, cur, g->n_full, g->sample_idx, g->n, qc ? qc->maf_thr : 0.0f,
+            rc = jxb::launch_count_qc(dummy, pk, bps, cur, g->n_full, g->sample_idx, g->n, qc ? qc->maf_thr : 0.0f,
                                       qc ? qc->miss_thr : 1.0f, qc ? qc->het_thr : 0.0f, g->counts, g->af, g->miss, g->st);
             jxb::note_launch(1);
             if (rc) return rc;
-            JXB_CUDA_OK(cudaMemcpyAsync(af_host.data(), g->af, cur * sizeof(float), cudaMemcpyDeviceToHost, g->st));
             if (qc) {
                 counts_host.resize(cur * 4);
                 JXB_CUDA_OK(cudaMemcpyAsync(counts_host.data(), g->counts, cur * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, g->st));
             }
         }
-        const bool masked = !row_maf_host && qc;
-        rc = jxb::update_device(*g, g->packed, bps, cur, g->af, masked ? g->counts : nullptr);
+        JXB_CUDA_OK(cudaMemcpyAsync(af_host.data(), g->af, cur * sizeof(float), cudaMemcpyDeviceToHost, g->st));
+        const bool masked = !row_maf && qc;
+        rc = jxb::update_device(*g, pk, bps, cur, g->af, masked ? g->counts : nullptr);
         if (rc) return rc;
         JXB_CUDA_OK(cudaStreamSynchronize(g->st));
         // grm.rs:91-111 / decode.rs:813-815, 842: var = 2p(1-p) in f32, summed in f64 in SNP order
@@ -526,6 +529,16 @@ extern "C" int jxb_grm_update(jxb_grm* h, const uint8_t* packed_host, size_t bps
         g->snps += cur;
     }
     return 0;
+}
+
+extern "C" int jxb_grm_update(jxb_grm* h, const uint8_t* packed_host, size_t bps, size_t rows,
+                              const float* row_maf_host, const jxb_qc_cfg* qc) {
+    return grm_update_impl((GrmHandle*)h, packed_host, false, bps, rows, row_maf_host, qc);
+}
+
+extern "C" int jxb_grm_update_dev(jxb_grm* h, const uint8_t* packed_dev, size_t bps, size_t rows,
+                                  const float* row_maf_dev, const jxb_qc_cfg* qc) {
+    return grm_update_impl((GrmHandle*)h, packed_dev, true, bps, rows, row_maf_dev, qc);
 }
 
 extern "C" int jxb_grm_finish(jxb_grm* h, double* k_host, double* varsum_out) {

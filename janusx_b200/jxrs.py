@@ -930,6 +930,19 @@ class DeviceGrm:
         check(lib().jxb_grm_update(self.handle, ptr(packed), packed.shape[1], packed.shape[0], ptr(maf),
                                    C.byref(cfg) if cfg is not None else None))
 
+    def update_dev(self, packed_dev_ptr: int, rows: int, bps: int, row_maf_dev_ptr=None, qc=None) -> None:
+        """Same as update() for packed rows already in HBM on this handle's device (raw device pointers)."""
+        cfg = None if qc is None else QcCfg(float(qc[0]), float(qc[1]), float(qc[2]), 0)
+        check(lib().jxb_grm_update_dev(self.handle, packed_dev_ptr, int(bps), int(rows), row_maf_dev_ptr,
+                                       C.byref(cfg) if cfg is not None else None))
+
+    def eigh_dev(self, evals_dev_ptr: int, ut_f32_dev_ptr: int, diag_shift: float = 1e-6) -> None:
+        """Finish, then decompose in place with outputs left on the device (f64[n], f32[n, n] caller buffers)."""
+        self.finish(to_host=False)
+        check(lib().jxb_eigh_dev(self.device, self.n, lib().jxb_grm_device_matrix(self.handle), float(diag_shift),
+                                 evals_dev_ptr, ut_f32_dev_ptr, lib().jxb_grm_stream(self.handle)))
+        check(lib().jxb_grm_finish(self.handle, None, None))   # synchronises the handle's stream
+
     @property
     def rows_used(self) -> int:
         return int(lib().jxb_grm_rows_used(self.handle))
