@@ -76,12 +76,13 @@ def gen_packed_batch(torch, n, rows, batch_index, device, want_dosage=False):
     return packed, (torch.cat(dos_all) if want_dosage else None)
 
 
-def build_null_model(torch, n, grm_snps, q, device, timings):
+def build_null_model(torch, n, grm_snps, q, device, timings=None):
     """Null-model inputs through the library's own front steps: centred VanRaden GRM of `grm_snps` synthetic SNPs on
     the int8 tensor cores (csrc/grm.cu; src/stats/grm.rs:204-608), K + 1e-6 I decomposed in place by cuSOLVER
     (csrc/eigh.cu; workflow_model_stream.py:902).  Phenotype 100 + G beta + e at pve 0.5, q N(0,1)
     covariates.  Returns host arrays (s, X design, y) and U^T as an f32 device tensor (pyBLUP/assoc.py:1818)."""
     from janusx_b200 import jxrs
+    timings = {} if timings is None else timings
     grm = jxrs.DeviceGrm(n, None, 1, device.index or 0)
     gv = torch.zeros(n, dtype=torch.float64, device=device)
     gt = torch.Generator(device=device)
