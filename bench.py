@@ -36,8 +36,8 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=int(os.environ.get("JXB_BENCH_N", 20000)))
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("JXB_BENCH_BATCH", 56832)),
-                    help="SNPs per step; 56832 = 148 SMs x 12 warps x 32 SNPs = one full wave of the thread-per-SNP solve")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("JXB_BENCH_BATCH", 75776)),
+                    help="SNPs per step; 75776 = 148 SMs x 16 warps x 32 SNPs = one full wave of the thread-per-SNP solve")
     ap.add_argument("--model", default=os.environ.get("JXB_BENCH_MODEL", "lmm2"), choices=["lmm", "lmm2", "fvlmm"])
     ap.add_argument("--grm-snps", type=int, default=int(os.environ.get("JXB_BENCH_GRM_SNPS", 50000)))
     ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("JXB_BENCH_CPU_SAMPLE", 1024)))

@@ -27,8 +27,8 @@ from ._cabi import BedScanCfg, JxbError, QcCfg, SolveCfg, check, lib, ptr
 
 MODEL_CODES = {"add": 0, "dom": 1, "rec": 2, "het": 3}
 # SNP rows per device batch of the file-level scans: one full wave of the thread-per-SNP solve kernel on a
-# 148-SM B200 (148 SMs x 12 warps x 32 SNPs).  The reference's rotate_block_rows (default 512) sizes CPU tiles.
-DEFAULT_DEVICE_BATCH = 56832
+# 148-SM B200 (148 SMs x 16 warps x 32 SNPs).  The reference's rotate_block_rows (default 512) sizes CPU tiles.
+DEFAULT_DEVICE_BATCH = 75776
 
 __all__ = [
     "DeviceModel", "lmm_reml_chunk_f32", "lmm_reml_chunk_from_snp_f32", "lmm_reml_lmm2_chunk_from_snp_f32",
