@@ -83,6 +83,16 @@ def build_null_model(torch, n, grm_snps, q, device, timings=None):
     covariates.  Returns host arrays (s, X design, y) and U^T as an f32 device tensor (pyBLUP/assoc.py:1818)."""
     from janusx_b200 import jxrs
     timings = {} if timings is None else timings
+    if n > 46340:
+        # cuSOLVER's Xsyevd rejects n*n >= 2^31: model two unrelated populations (block-diagonal GRM and U^T)
+        h = n // 2
+        s1, u1, X1, y1 = build_null_model(torch, h, grm_snps, q, device, timings)
+        s2, u2, X2, y2 = build_null_model(torch, n - h, max(1024, grm_snps // 2), q, device)
+        u_t = torch.zeros((n, n), dtype=torch.float32, device=device)
+        u_t[:h, :h] = u1
+        u_t[h:, h:] = u2
+        timings["blocks"] = 2
+        return np.concatenate([s1, s2]), u_t, np.concatenate([X1, X2]), np.concatenate([y1, y2])
     grm = jxrs.DeviceGrm(n, None, 1, device.index or 0)
     gv = torch.zeros(n, dtype=torch.float64, device=device)
     gt = torch.Generator(device=device)

@@ -63,6 +63,9 @@ __global__ void narrow_kernel(const double* __restrict__ src, float* __restrict_
 
 int eigh_device(int device, size_t n, double* a_dev, double diag_shift, double* evals_dev, float* ut_f32_dev,
                 cudaStream_t st) {
+    if (n > 46340)
+        return fail(-115, "eigendecomposition of n=" + std::to_string(n) + " is beyond cusolverDnXsyevd (it rejects n*n >= 2^31, "
+                          "i.e. n > 46340); decompose on the host or per population block and pass (S, U^T) to jxb_model_create");
     Solver& s = solver();
     if (!s.ok) return fail(-110, "libcusolver (cusolverDnXsyevd) could not be loaded: the eigendecomposition has no CPU fallback");
     JXB_CUDA_OK(cudaSetDevice(device));
@@ -90,9 +93,12 @@ int eigh_device(int device, size_t n, double* a_dev, double diag_shift, double* 
     if (s.create_params(&prm) != CUSOLVER_STATUS_SUCCESS) return done(-111, "cusolverDnCreateParams failed");
     size_t bytes_dev = 0, bytes_host = 0;
     // symmetric input: "lower, column-major" of the row-major buffer is its upper triangle -- either is the matrix
-    if (s.buffer_size(h, prm, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int64_t)n, CUDA_R_64F, a_dev,
-                      (int64_t)n, CUDA_R_64F, evals_dev, CUDA_R_64F, &bytes_dev, &bytes_host) != CUSOLVER_STATUS_SUCCESS)
-        return done(-112, "cusolverDnXsyevd_bufferSize failed");
+    const cusolverStatus_t sb = s.buffer_size(h, prm, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int64_t)n,
+                                              CUDA_R_64F, a_dev, (int64_t)n, CUDA_R_64F, evals_dev, CUDA_R_64F,
+                                              &bytes_dev, &bytes_host);
+    if (sb != CUSOLVER_STATUS_SUCCESS)
+        return done(-112, "cusolverDnXsyevd_bufferSize failed with status " + std::to_string((int)sb) + " (n=" +
+                              std::to_string(n) + ")");
     if (cudaMalloc(&ws_dev, bytes_dev ? bytes_dev : 16) != cudaSuccess || cudaMalloc((void**)&info_dev, sizeof(int)) != cudaSuccess) {
         cudaGetLastError();
         return done(-100, "eigh workspace allocation of " + std::to_string(bytes_dev) + " bytes failed");

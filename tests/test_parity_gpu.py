@@ -531,6 +531,64 @@ def test_full_size_n20000_parity_sample(jx, oracle):
         np.testing.assert_allclose(out[:, 4], want[:, 4], rtol=1e-10)
 
 
+def test_full_batch_at_full_size_sampled_parity(jx, oracle):
+    """One full device batch (75,776 SNP rows = the bench step) at n = 20,000 (JXB_TEST_FULL_N=50000 for BASELINE
+    configs[3]): rows sampled from the start, middle and end of the batch are checked against the oracle, which
+    catches 32-bit index overflow in any kernel (rows x n exceeds 2^31 at n = 50,000)."""
+    import os
+    import sys
+    from pathlib import Path
+    import torch
+    root = str(Path(__file__).resolve().parents[1])
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    import bench as B
+    n = int(os.environ.get("JXB_TEST_FULL_N", 20000))
+    rows, q = 75776, 3
+    dev = torch.device("cuda:0")
+    if n <= 46340:
+        s_np, u_t_dev, X_np, y_np = B.build_null_model(torch, n, 4096, q, dev)
+    else:
+        # cuSOLVER's Xsyevd rejects n*n >= 2^31: two unrelated half-size populations = block-diagonal GRM / U^T
+        h = n // 2
+        s1, u1, X1, y1 = B.build_null_model(torch, h, 4096, q, dev)
+        s2, u2, X2, y2 = B.build_null_model(torch, n - h, 2048, q, dev)
+        u_t_dev = torch.zeros((n, n), dtype=torch.float32, device=dev)
+        u_t_dev[:h, :h] = u1
+        u_t_dev[h:, h:] = u2
+        del u1, u2
+        s_np, X_np, y_np = np.concatenate([s1, s2]), np.concatenate([X1, X2]), np.concatenate([y1, y2])
+    ut = u_t_dev.cpu().numpy()
+    mdl = jx.DeviceModel(s_np, np.ones((n, q + 1)), np.zeros(n), u_t_dev, device=0, u_t_on_device=True)
+    del u_t_dev
+    torch.cuda.empty_cache()
+    xo, yo = oracle.lmm_rotate_x_y_with_ut_f64(ut, X_np, y_np)
+    mdl.set_xy(xo, yo[:, 0])
+    lbd_o, _, _ = oracle.lmm_reml_null_f32(s_np, xo, yo[:, 0], -5.0, 5.0, 50, 1e-3)
+    l10 = float(np.log10(lbd_o))
+    lo, hi = l10 - 2.0, l10 + 2.0
+    _, nullml = oracle.lmm_ml_null_brent(s_np, xo, yo[:, 0], lo, hi, 30, 1e-2, l10)
+    pk, _ = B.gen_packed_batch(torch, n, rows, 4242, dev)
+    bps = pk.shape[1]
+    torch.cuda.synchronize(dev)          # the scan runs on the model's own stream
+    cols = mdl.scan_packed_dev(pk.data_ptr(), rows, bps, n, None, mode="lmm2", low=lo, high=hi, init=l10, nullml=nullml)
+    keep, af, missing, out, ev = mdl.scan_fetch(rows, cols)
+    assert keep.sum() == out.shape[0], (int(keep.sum()), out.shape)
+    assert keep.sum() > rows * 0.99, int(keep.sum())
+    pos = np.cumsum(keep) - 1                                   # source row -> compacted row
+    picks = [r for r in list(range(0, 6)) + list(range(rows // 2, rows // 2 + 6)) + list(range(rows - 6, rows)) if keep[r]]
+    sub = pk[picks].cpu().numpy()
+    keep_o, af_o, _, miss_o = oracle.count_qc_block(sub, n, None, 0.02, 0.05, 1.0)
+    assert keep_o.all() and np.array_equal(af_o.view(np.uint32), af[picks].view(np.uint32))
+    assert np.array_equal(miss_o, missing[picks])
+    g = oracle.decode_centered_block(sub, n, af_o)
+    want = oracle.lmm_reml_lmm2_chunk_f32(s_np, xo, yo[:, 0], lo, hi, oracle.rotate_block(g, ut), nullml, 30, 1e-2,
+                                          init_reml=l10)
+    got = out[pos[picks]]
+    assert_results_close(got, want, cols_p=(2, 5), cols_lambda=(3,))
+    np.testing.assert_allclose(got[:, 4], want[:, 4], rtol=1e-10)
+
+
 def test_cli_gwas_lmm_end_to_end(jx, oracle, tmp_path):
     """`python -m janusx_b200.gwas` with the reference's flag names writes the reference TSV schema and naming;
     rows agree with the oracle run on the same null model."""
