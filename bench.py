@@ -384,20 +384,29 @@ def main():
         solve_flop = mean_evals * flop_per_eval * kept
         solve_s = st["solve"] * 1e-3
         fp64_core_peak = 36.0      # TFLOP/s: 18.0 T DFMA/s measured with tools/fp64_probe.cu (profiles/r1_fp64_probe.txt)
+        # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu capture of this
+        # exact default workload (profiles/r1_ncu_final_metrics.csv); null for any other configuration
+        default_cfg = (n == 20000 and B == 75776 and args.model == "lmm2" and args.rotate_variant == 3 and q == 3)
+        solve_traffic = 468759369472 + 28234240 if default_cfg else None
+        rot_traffic = (76375571200 + 12103506432 + 171910203648 + 6066589696) if default_cfg else None
         rot_roof = {"kernel": ("rotate_dmma_kernel (FP64 DMMA GEMM)" if args.rotate_variant == 0 else
                                ("i8_rotate_kernel (tcgen05 int8-sliced exact rotation, 2 passes)" if args.rotate_variant == 3 else
                                 "int8-sliced exact rotation (10 cuBLASLt slice GEMMs + recombine_kernel)")),
                     "bound": "tensor", "achieved": rot_flop / rot_s / 1e12 if rot_s > 0 else 0.0, "peak": fp64_peak,
                     "unit": "TFLOP/s (FP64-equivalent)", "frac": (rot_flop / rot_s / 1e12 / fp64_peak) if rot_s > 0 and fp64_peak > 0 else None,
-                    "traffic": None, "launch_ms": st["rotate"],
+                    "traffic": rot_traffic, "launch_ms": st["rotate"],
                     "peak_source": "cuBLAS DGEMM (M=4096,N=K=n) measured in this run; MEASURED_PEAKS.json holds no FP64 "
                                    "figure. frac > 1 for the int8-sliced variant: same f64-accurate result from 10 exact "
                                    "int8 slice GEMMs (" + f"{10 * rot_flop / rot_s / 1e12:.0f}" + " int8 TOP/s of 4500 nominal)"}
         solve_roof = {"kernel": (f"solve_thread_kernel<{p}>" if (args.rotate_variant == 3 and kept >= 32768) else f"solve_warp_kernel<{p}>") + " (per-SNP REML/ML Brent, FP64 CUDA cores)", "bound": "fp64-cuda-core",
                       "achieved": solve_flop / solve_s / 1e12 if solve_s > 0 else 0.0, "peak": fp64_core_peak,
                       "unit": "TFLOP/s", "frac": (solve_flop / solve_s / 1e12 / fp64_core_peak) if solve_s > 0 else None,
-                      "traffic": None, "launch_ms": st["solve"],
+                      "traffic": solve_traffic, "launch_ms": st["solve"],
                       "algorithmic_flop_per_launch": solve_flop,
+                      "algorithmic_bytes_per_launch": (mean_evals * 2.0 + 1.0) * kept * n * 4.0,
+                      "traffic_source": "profiles/r1_ncu_final_metrics.csv (ncu, same command); algorithmic bytes = the f32 "
+                                        "rotated block streamed twice per objective evaluation (sums pass + residual pass) "
+                                        "plus once for the validity check",
                       "peak_source": "2 x 18.0 T DFMA/s measured on this pool's B200 (tools/fp64_probe.cu); the algorithmic "
                                      "count charges 1 flop per divide / log, which cost 9.5 / 51 DFMA-equivalents"}
         dominant = solve_roof if st["solve"] >= st["rotate"] else rot_roof
