@@ -220,6 +220,12 @@ double* jxb_grm_device_matrix(jxb_grm* g); /* f64[n,n] on the handle's device; v
 void* jxb_grm_stream(jxb_grm* g);          /* the cudaStream_t the handle's work is ordered on */
 void jxb_grm_destroy(jxb_grm* g);
 
+/* N3  VCF(.gz) -> PLINK BED/BIM/FAM, the one-off conversion in front of a `-vcf` scan (VcfSnpIter::next_snp_raw,
+ *     src/io/gfcore.rs:2875-2980; plink2bits_from_g_f32, src/io/gfreader.rs:2630-2641).  GT strings 0/0 0|0 -> 00,
+ *     0/1 1/0 0|1 1|0 -> 10, 1/1 1|1 -> 11, anything else -> 01 (missing); dosage counts ALT, BIM col 5 = REF, col 6 =
+ *     ALT; ID "." or empty -> chrom_pos.  snps_only drops sites whose REF/ALT are not single A/C/G/T.  Host only. */
+int jxb_vcf_to_plink(const char* vcf_path, const char* out_prefix, int snps_only, size_t* n_samples, size_t* n_sites);
+
 /* N2  eigendecomposition: rust_eigh_from_array_f64[_inplace] (src/math/eigh.rs:1621-1705, 1883-1990).  One
  *     cuSOLVER call (cusolverDnXsyevd, dlopen).  a f64[n,n] symmetric; diag_shift is added to the diagonal first (the
  *     reference's 1e-6 ridge, workflow_model_stream.py:902).  Eigenvalues ascending; the matrix is returned as U^T

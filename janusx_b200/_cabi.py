@@ -96,6 +96,7 @@ SYMBOLS = {
     "jxb_grm_device_matrix": (_vp, [_vp]),
     "jxb_grm_stream": (_vp, [_vp]),
     "jxb_grm_destroy": (None, [_vp]),
+    "jxb_vcf_to_plink": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, _psz, _psz]),
     "jxb_grm_eigh": (C.c_int, [_vp, C.c_double, _vp, _vp]),
     "jxb_eigh": (C.c_int, [C.c_int, C.c_size_t, _vp, C.c_double, _vp, _vp, _vp]),
     "jxb_eigh_dev": (C.c_int, [C.c_int, C.c_size_t, _vp, C.c_double, _vp, _vp, _vp]),

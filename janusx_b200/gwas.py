@@ -1,9 +1,9 @@
-"""`jx gwas`-compatible command line for the exact-LMM path only (-lmm / -lmm2 / -fvlmm on -bfile input).
+"""`jx gwas`-compatible command line for the exact-LMM path only (-lmm / -lmm2 / -fvlmm on -bfile / -vcf input).
 
 Flag names, defaults and the output naming follow python/janusx/assoc/workflow.py:6599-7047
 (`{out}/{prefix}.{trait}.{model}.tsv`, workflow_model_stream.py:992).  The scan itself is ONE call into the
 B200 library per trait (jxrs.*_bed_to_tsv_f32), exactly where the reference makes its one Rust call
-(workflow_model_stream.py:1449-1488).  Everything the reference CLI does outside this path (VCF/HMP input,
+(workflow_model_stream.py:1449-1488).  Everything the reference CLI does outside this path (HMP/TXT input,
 FarmCPU, plots, run history, -mem budgeting, LM switch) is out of scope; unsupported flags fail loudly.
 
   python -m janusx_b200.gwas -bfile panel -p pheno.tsv -n 0 -lmm -k 1 -q 3 -o out -prefix run1
@@ -27,7 +27,8 @@ def parse_args(argv: Optional[List[str]] = None) -> argparse.Namespace:
     ap = argparse.ArgumentParser(prog="jx gwas (janusx_b200)", description=__doc__,
                                  formatter_class=argparse.RawDescriptionHelpFormatter)
     g = ap.add_argument_group("Genotype Arguments")
-    g.add_argument("-bfile", "--bfile", required=True, help="PLINK prefix (.bed/.bim/.fam)")
+    g.add_argument("-bfile", "--bfile", default=None, help="PLINK prefix (.bed/.bim/.fam)")
+    g.add_argument("-vcf", "--vcf", default=None, help="VCF / VCF.gz (GT); converted once to a PLINK cache next to the output")
     p = ap.add_argument_group("Phenotype Arguments")
     p.add_argument("-p", "--pheno", required=True, help="phenotype table: first column sample IDs, header row")
     p.add_argument("-n", "--ncol", action="append", default=None, help="zero-based trait column(s); default all")
@@ -52,7 +53,27 @@ def parse_args(argv: Optional[List[str]] = None) -> argparse.Namespace:
     args = ap.parse_args(argv)
     if not (args.lmm or args.lmm2 or args.fvlmm):
         ap.error("select at least one of -lmm, -lmm2, -fvlmm (other models are outside this build's scope)")
+    if (args.bfile is None) == (args.vcf is None):
+        ap.error("give exactly one of -bfile, -vcf")
     return args
+
+
+def _vcf_cache(vcf: str, out_dir: str, snps_only: bool) -> str:
+    """VCF -> PLINK cache (assoc/workflow.py:2431-2477: rebuilt when missing or older than the source)."""
+    from . import jxrs
+    base = os.path.basename(vcf)
+    for ext in (".vcf.gz", ".vcf"):
+        if base.lower().endswith(ext):
+            base = base[: -len(ext)]
+            break
+    prefix = os.path.join(out_dir, f"~{base}.snp{1 if snps_only else 0}")
+    targets = [prefix + e for e in (".bed", ".bim", ".fam")]
+    fresh = all(os.path.isfile(t) for t in targets) and min(os.path.getmtime(t) for t in targets) >= os.path.getmtime(vcf)
+    if not fresh:
+        t0 = time.time()
+        ns, nv = jxrs.vcf_to_plink(vcf, prefix, snps_only)
+        print(f"[vcf] {vcf}: {ns} samples x {nv} sites -> {prefix}.bed ({time.time() - t0:.2f} s)", file=sys.stderr)
+    return prefix
 
 
 def _read_table(path: str):
@@ -95,11 +116,13 @@ def main(argv: Optional[List[str]] = None) -> int:
     from . import assoc, jxrs
 
     t0 = time.time()
+    os.makedirs(args.out, exist_ok=True)
+    if args.vcf is not None:
+        args.bfile = _vcf_cache(args.vcf, args.out, args.snps_only)
     fam = _read_fam(args.bfile)
     ids_p, traits, Y = _read_table(args.pheno)
     cols = list(range(len(traits))) if not args.ncol else [int(c) for tok in args.ncol for c in str(tok).split(",")]
-    prefix = args.prefix or os.path.basename(args.bfile)
-    os.makedirs(args.out, exist_ok=True)
+    prefix = args.prefix or os.path.basename(args.vcf or args.bfile).replace(".vcf.gz", "").replace(".vcf", "")
     outprefix = os.path.join(args.out, prefix)
 
     if args.grm == "1":

@@ -1050,6 +1050,15 @@ def rust_eigh_from_array_f64(a, threads=0, driver=None, jobz="V", require_lapack
 rust_eigh_from_array_f64_inplace = rust_eigh_from_array_f64
 
 
+def vcf_to_plink(vcf_path, out_prefix, snps_only=False):
+    """VCF(.gz) -> out_prefix.bed/.bim/.fam with the reference's GT rules (src/io/gfcore.rs:2875-2980); host only.
+    -> (n_samples, n_sites)."""
+    ns, nv = C.c_size_t(), C.c_size_t()
+    check(lib().jxb_vcf_to_plink(str(vcf_path).encode(), str(out_prefix).encode(), 1 if snps_only else 0,
+                                 C.byref(ns), C.byref(nv)))
+    return int(ns.value), int(nv.value)
+
+
 def gwas_lmm_lm_null_lrt_decision(y, x_cov, lmm_ml0, alpha=0.05, boundary_mixture=True):
     """src/stats/gwas_unified.rs:119-175 -> (switch_to_lm, lrt_stat, pval, lm_ml0).
 
