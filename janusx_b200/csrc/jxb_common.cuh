@@ -104,8 +104,6 @@ int launch_widen_f32(const float* src, size_t ld_src, size_t rows, size_t n, dou
 // out: transposed ? rotT-style [n][ld] : row-major [rows][ld]
 int launch_rotate(Model& m, size_t max_rows, const int32_t* n_rows_dev, float* out, size_t ld, int transposed,
                   cudaStream_t st, int variant);
-int launch_transpose_f32(const float* src, size_t ld_src, size_t rows, size_t cols, float* dst, size_t ld_dst,
-                         cudaStream_t st);  // dst[c][r] = src[r][c]
 int launch_rotate_xy(const Model& m, const float* ut_f32, const double* x, size_t q, const double* y,
                      double* x_rot, double* y_rot, cudaStream_t st);
 int launch_solve(const Model& m, const float* g_rot, size_t ldc, size_t max_rows, const int32_t* n_rows_dev,

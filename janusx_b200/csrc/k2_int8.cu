@@ -16,8 +16,9 @@
 // pure f32-rounding residual (|.| <= 2e-7), so T_2 only needs its top 3 digits.
 //
 // This file holds: the one-off slicing of U^T, the int8 decode of packed genotypes, the f64 recombination, and
-// the slice GEMMs.  Round 1 runs the slice GEMMs through cuBLASLt (IMMA/tcgen05 int8, loaded with dlopen so the
-// library stays optional); the hand-written tcgen05 kernel that fuses slices and recombination replaces it next.
+// the slice GEMMs of rotation variant 2, which run through cuBLASLt (int8 tensor cores, loaded with dlopen so the
+// library stays optional).  The default variant 3 (k2_i8mma.cu) shares the slicing and the decode with this file and
+// replaces the library GEMMs + recombination kernel by one hand-written tcgen05 kernel per pass.
 #include <cublasLt.h>
 #include <dlfcn.h>
 

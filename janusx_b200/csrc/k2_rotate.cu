@@ -290,21 +290,6 @@ __global__ void __launch_bounds__(256) rotate_xy_kernel(const double* __restrict
     }
 }
 
-__global__ void transpose_f32_kernel(const float* __restrict__ src, size_t ld_src, int rows, int cols,
-                                     float* __restrict__ dst, size_t ld_dst) {
-    __shared__ float tile[32][33];
-    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
-    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
-        const int r = r0 + k, c = c0 + threadIdx.x;
-        tile[k][threadIdx.x] = (r < rows && c < cols) ? src[(size_t)r * ld_src + c] : 0.0f;
-    }
-    __syncthreads();
-    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
-        const int c = c0 + k, r = r0 + threadIdx.x;
-        if (r < rows && c < cols) dst[(size_t)c * ld_dst + r] = tile[threadIdx.x][k];
-    }
-}
-
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -374,15 +359,6 @@ int launch_rotate(Model& m, size_t max_rows, const int32_t* n_rows_dev, float* o
     rotate_dmma_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(*(const CUtensorMap*)m.tmap_g, *(const CUtensorMap*)m.tmap_ut,
                                                           out, ld, transposed, (int)m.n, kblocks, (int)max_rows,
                                                           n_rows_dev);
-    JXB_CUDA_OK(cudaGetLastError());
-    return 0;
-}
-
-int launch_transpose_f32(const float* src, size_t ld_src, size_t rows, size_t cols, float* dst, size_t ld_dst,
-                         cudaStream_t st) {
-    if (rows == 0 || cols == 0) return 0;
-    dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32)), block(32, 8);
-    transpose_f32_kernel<<<grid, block, 0, st>>>(src, ld_src, (int)rows, (int)cols, dst, ld_dst);
     JXB_CUDA_OK(cudaGetLastError());
     return 0;
 }
