@@ -203,19 +203,31 @@ def measure_fp64_peak(torch, device, n):
 # ------------------------------------------------------------------------------------------------------
 # CPU reference arm (oracle port)
 # ------------------------------------------------------------------------------------------------------
-def cpu_scan(O, packed_rows, n, s, xcov, y, ut_f32, low, high, model, nullml, l10):
+def cpu_scan(O, packed_rows, n, s, xcov, y, ut_f32, low, high, model, nullml, l10, stages=None):
     """One pass of the reference algorithm on the host: count/QC, decode, f32 GEMM rotation (numpy/OpenBLAS,
-    all cores -- the reference's cblas_sgemm stage), per-SNP solve (OpenMP, one SNP per task)."""
+    all cores -- the reference's cblas_sgemm stage), per-SNP solve (OpenMP, one SNP per task).  `stages` (a dict)
+    accumulates seconds per stage."""
+    t = [time.perf_counter()]
+
+    def lap(name):
+        t.append(time.perf_counter())
+        if stages is not None:
+            stages[name] = stages.get(name, 0.0) + (t[-1] - t[-2])
+
     keep, af, mr, missing = O.count_qc_block(packed_rows, n, None, 0.02, 0.05, 1.0)
     idx = np.nonzero(keep)[0]
+    lap("count_qc")
     g = O.decode_centered_block(packed_rows, n, af[idx], row_indices=idx)
+    lap("decode")
     rot = g @ ut_f32.T
+    lap("rotate")
     if model == "lmm2":
         out = O.lmm_reml_lmm2_chunk_f32(s, xcov, y, low, high, rot, nullml, 30, 1e-2, 0, init_reml=l10)
     elif model == "fvlmm":
         out, _ = O.lmm_assoc_chunk_f32(s, xcov, y, l10, rot, 0, None)
     else:
         out = O.lmm_reml_chunk_f32(s, xcov, y, low, high, rot, 30, 1e-2, 0, None)
+    lap("solve")
     return out
 
 
@@ -448,10 +460,12 @@ def cpu_baseline(args, n, B, s_np, xcov, y, ut, packed_host, low, high, nullml, 
     from oracle import oracle as O
     O.build()
     rows = min(args.cpu_sample, B)
+    stages = {}
     t0 = time.perf_counter()
-    cpu_scan(O, packed_host[:rows], n, s_np, xcov, y, ut, low, high, args.model, nullml, l10)
+    cpu_scan(O, packed_host[:rows], n, s_np, xcov, y, ut, low, high, args.model, nullml, l10, stages)
     dt = time.perf_counter() - t0
     return {"value": rows / dt, "unit": "SNPs/s", "cores": O.max_threads(), "kind": "port",
+            "stage_s": {k: round(v, 4) for k, v in stages.items()},
             "sample": f"{rows} SNPs of the same batch (count/QC + decode + f32 OpenBLAS rotation + OpenMP per-SNP "
                       f"{args.model} solve), {dt:.1f} s"}
 
@@ -477,9 +491,10 @@ def run_reference(args, torch, config, n, B, q, s_np, X_np, y_np, u_t_dev, u_t_h
         packed, _ = synth.draw_genotypes(rows, n, seed=SEED)
     for _ in range(max(0, min(args.warmup, 1))):
         cpu_scan(O, packed[: max(8, rows // 16)], n, s_np, xcov, y, ut, low, high, args.model, nullml, l10)
+    stages = {}
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_scan(O, packed, n, s_np, xcov, y, ut, low, high, args.model, nullml, l10)
+        cpu_scan(O, packed, n, s_np, xcov, y, ut, low, high, args.model, nullml, l10, stages)
     dt = time.perf_counter() - t0
     value = rows * args.steps / dt
     cores = O.max_threads()
@@ -490,6 +505,7 @@ def run_reference(args, torch, config, n, B, q, s_np, X_np, y_np, u_t_dev, u_t_h
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 rotation / f64 solve",
             "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": value, "unit": "SNPs/s", "cores": cores, "kind": "port",
+                             "stage_s": {k: round(v, 4) for k, v in stages.items()},
                              "sample": f"{rows} SNPs per step (bounded sample of the {B}-SNP batch)"},
             "e2e": {"value": value, "unit": "SNPs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "CPU restatement of the reference algorithm (the Rust reference cannot be built in this image)"}
