@@ -36,8 +36,9 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=int(os.environ.get("JXB_BENCH_N", 20000)))
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("JXB_BENCH_BATCH", 75776)),
-                    help="SNPs per step; 75776 = 148 SMs x 16 warps x 32 SNPs = one full wave of the thread-per-SNP solve")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("JXB_BENCH_BATCH", 0)),
+                    help="SNPs per step; default = the library's device batch: 151,552 (two waves of 148 SMs x 16 warps x "
+                         "32 SNPs of the thread-per-SNP solve) for n <= 24,000, else 75,776")
     ap.add_argument("--model", default=os.environ.get("JXB_BENCH_MODEL", "lmm2"), choices=["lmm", "lmm2", "fvlmm"])
     ap.add_argument("--grm-snps", type=int, default=int(os.environ.get("JXB_BENCH_GRM_SNPS", 50000)))
     ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("JXB_BENCH_CPU_SAMPLE", 1024)))
@@ -242,6 +243,9 @@ def main():
     import torch
 
     n, B, q = args.n, args.batch, 3
+    if B <= 0:
+        B = 2 * 75776 if n <= 24000 else 75776          # janusx_b200.jxrs.default_device_batch
+        args.batch = B
     p = q + 1
     config = {"workload": f"synthetic n={n}, m=1,000,000 job sampled in batches of {B} SNPs, -{args.model} "
                           f"(Wald{' + LRT' if args.model == 'lmm2' else ''}), 1 trait, {q} covariates "
@@ -398,9 +402,11 @@ def main():
         fp64_core_peak = 36.0      # TFLOP/s: 18.0 T DFMA/s measured with tools/fp64_probe.cu (profiles/r1_fp64_probe.txt)
         # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu capture of this
         # exact default workload (profiles/r1_ncu_final_metrics.csv); null for any other configuration
-        default_cfg = (n == 20000 and B == 75776 and args.model == "lmm2" and args.rotate_variant == 3 and q == 3)
-        solve_traffic = 468759369472 + 28234240 if default_cfg else None
-        rot_traffic = (76375571200 + 12103506432 + 171910203648 + 6066589696) if default_cfg else None
+        # (captured at one 75,776-SNP wave; the default step is two waves, so bytes scale by kept / 75,734)
+        default_cfg = (n == 20000 and B % 75776 == 0 and args.model == "lmm2" and args.rotate_variant == 3 and q == 3)
+        waves = kept / 75734.0
+        solve_traffic = (468759369472 + 28234240) * waves if default_cfg else None
+        rot_traffic = (76375571200 + 12103506432 + 171910203648 + 6066589696) * waves if default_cfg else None
         rot_roof = {"kernel": ("rotate_dmma_kernel (FP64 DMMA GEMM)" if args.rotate_variant == 0 else
                                ("i8_rotate_kernel (tcgen05 int8-sliced exact rotation, 2 passes)" if args.rotate_variant == 3 else
                                 "int8-sliced exact rotation (10 cuBLASLt slice GEMMs + recombine_kernel)")),

@@ -26,9 +26,16 @@ from . import _cabi
 from ._cabi import BedScanCfg, JxbError, QcCfg, SolveCfg, check, lib, ptr
 
 MODEL_CODES = {"add": 0, "dom": 1, "rec": 2, "het": 3}
-# SNP rows per device batch of the file-level scans: one full wave of the thread-per-SNP solve kernel on a
-# 148-SM B200 (148 SMs x 16 warps x 32 SNPs).  The reference's rotate_block_rows (default 512) sizes CPU tiles.
+# SNP rows per device batch of the file-level scans.  75,776 = one full wave of the thread-per-SNP solve kernel on a
+# 148-SM B200 (148 SMs x 16 warps x 32 SNPs); two waves per batch hide most of the wave's ragged tail (Brent paths of
+# different length): +2.9 % at n = 20,000.  Per-batch workspace is ~300 bytes x n per row, so large n stays at one wave.
+# The reference's rotate_block_rows (default 512) sizes CPU tiles and has no meaning here.
 DEFAULT_DEVICE_BATCH = 75776
+
+
+def default_device_batch(n: int) -> int:
+    return 2 * DEFAULT_DEVICE_BATCH if n <= 24000 else DEFAULT_DEVICE_BATCH
+
 
 __all__ = [
     "DeviceModel", "lmm_reml_chunk_f32", "lmm_reml_chunk_from_snp_f32", "lmm_reml_lmm2_chunk_from_snp_f32",
@@ -534,7 +541,7 @@ def lmm_reml_assoc_bed_to_tsv_f32(bed_prefix, out_tsv, s, xcov, y_rot, u_t, maf_
     mdl = _get_model(s, xcov, y_rot, u_t)
     return mdl.scan_bed_to_tsv(bed_prefix, out_tsv, maf_thr, miss_thr, het_thr, genetic_model, snps_only, sample_ids,
                                "lmm", low, high, max_iter, tol, nullml, None, None, row_indices=rows_sel,
-                               batch_rows=max(int(rotate_block_rows), DEFAULT_DEVICE_BATCH), progress_callback=progress_callback,
+                               batch_rows=max(int(rotate_block_rows), default_device_batch(mdl.n)), progress_callback=progress_callback,
                                progress_every=progress_every)
 
 
@@ -565,7 +572,7 @@ def lmm_reml_lmm2_assoc_bed_to_tsv_f32(bed_prefix, out_tsv, s, xcov, y_rot, u_t,
     init = i_reml if i_reml is not None else i_ml
     return mdl.scan_bed_to_tsv(bed_prefix, out_tsv, maf_thr, miss_thr, het_thr, genetic_model, snps_only, sample_ids,
                                "lmm2", low, high, max_iter, tol, nullml, init, None, row_indices=rows_sel,
-                               batch_rows=max(int(rotate_block_rows), DEFAULT_DEVICE_BATCH), progress_callback=progress_callback,
+                               batch_rows=max(int(rotate_block_rows), default_device_batch(mdl.n)), progress_callback=progress_callback,
                                progress_every=progress_every)
 
 
@@ -583,7 +590,7 @@ def fvlmm_assoc_bed_to_tsv_f32(bed_prefix, out_tsv, s, xcov, y_rot, log10_lbd, u
     mdl = _get_model(s, xcov, y_rot, u_t)
     rows = mdl.scan_bed_to_tsv(bed_prefix, out_tsv, maf_thr, miss_thr, het_thr, genetic_model, snps_only, sample_ids,
                                "fvlmm", nullml=nullml, log10_lbd=log10_lbd, row_indices=rows_sel,
-                               batch_rows=max(int(rotate_block_rows), DEFAULT_DEVICE_BATCH), progress_callback=progress_callback,
+                               batch_rows=max(int(rotate_block_rows), default_device_batch(mdl.n)), progress_callback=progress_callback,
                                progress_every=progress_every)
     # fvlmm.rs:2746-2753: pve = clamp(1 - ypy / sum y^2, 0, 1)
     _, meta = mdl.fixed_chunk(np.zeros((1, mdl.n), dtype=np.float32), log10_lbd, rotated=True, return_meta=True)
@@ -763,7 +770,7 @@ def _scan_packed_all_rows(mdl, packed, n_samples, sidx, row_maf, model, low, hig
     out = np.zeros((m, cols), dtype=np.float64)
     af_all = np.zeros(m, dtype=np.float32)
     miss_all = np.zeros(m, dtype=np.int32)
-    step = DEFAULT_DEVICE_BATCH if not progress_every else max(1, min(int(progress_every), DEFAULT_DEVICE_BATCH))
+    step = default_device_batch(mdl.n) if not progress_every else max(1, min(int(progress_every), default_device_batch(mdl.n)))
     for r0 in range(0, m, step):
         r1 = min(m, r0 + step)
         keep, af, missing, res = mdl.scan_packed(packed[r0:r1], n_samples, sidx, None, 0.0, 1.0, 0.0, model, "lmm", low, high,

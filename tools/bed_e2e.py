@@ -38,7 +38,7 @@ out = str(tmp / "out.tsv")
 for rep in range(2):
     t1 = time.time()
     rows = mdl.scan_bed_to_tsv(prefix, out, 0.02, 0.05, 1.0, mode=model, low=l10 - 2, high=l10 + 2, init=l10,
-                               batch_rows=jxrs.DEFAULT_DEVICE_BATCH)
+                               batch_rows=jxrs.default_device_batch(n))
     dt = time.time() - t1
     print(json.dumps({"n": n, "m": m, "model": model, "rows": rows, "seconds": dt, "snps_per_s": m / dt,
                       "tsv_mb": os.path.getsize(out) / 1e6}), flush=True)
