@@ -416,13 +416,14 @@ def main():
                     "peak_source": "cuBLAS DGEMM (M=4096,N=K=n) measured in this run; MEASURED_PEAKS.json holds no FP64 "
                                    "figure. frac > 1 for the int8-sliced variant: same f64-accurate result from 10 exact "
                                    "int8 slice GEMMs (" + f"{10 * rot_flop / rot_s / 1e12:.0f}" + " int8 TOP/s of 4500 nominal)"}
-        solve_roof = {"kernel": (f"solve_thread_kernel<{p}>" if (args.rotate_variant == 3 and kept >= 32768) else f"solve_warp_kernel<{p}>") + " (per-SNP REML/ML Brent, FP64 CUDA cores)", "bound": "fp64-cuda-core",
+        solve_roof = {"kernel": (f"solve_lane_kernel<{p}>" if (args.rotate_variant >= 2 and kept >= 32768) else f"solve_warp_kernel<{p}>") + " (per-SNP REML/ML Brent, FP64 CUDA cores)", "bound": "fp64-cuda-core",
                       "achieved": solve_flop / solve_s / 1e12 if solve_s > 0 else 0.0, "peak": fp64_core_peak,
                       "unit": "TFLOP/s", "frac": (solve_flop / solve_s / 1e12 / fp64_core_peak) if solve_s > 0 else None,
                       "traffic": solve_traffic, "launch_ms": st["solve"],
                       "algorithmic_flop_per_launch": solve_flop,
                       "algorithmic_bytes_per_launch": (mean_evals * 2.0 + 1.0) * kept * n * 4.0,
-                      "traffic_source": "profiles/r1_ncu_final_metrics.csv (ncu, same command); algorithmic bytes = the f32 "
+                      "traffic_source": "profiles/r1_ncu_final_metrics.csv (ncu of solve_thread_kernel, which streams the same "
+                                        "bytes as the lane kernel); algorithmic bytes = the f32 "
                                         "rotated block streamed twice per objective evaluation (sums pass + residual pass) "
                                         "plus once for the validity check",
                       "peak_source": "2 x 18.0 T DFMA/s measured on this pool's B200 (tools/fp64_probe.cu); the algorithmic "

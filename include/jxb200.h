@@ -148,6 +148,9 @@ void jxb_set_rotate_variant(int variant);
 /* batches with at least this many kept SNPs use the one-thread-per-SNP solve kernel (default 32768);
  * smaller ones the warp-per-SNP kernel.  Both reproduce the reference summation order. */
 void jxb_set_thread_solve_min_rows(size_t rows);
+/* Kernel for those large batches: 0 (default) = lane-per-SNP with refill on the row-major block, 1 = the earlier
+ * thread-per-SNP kernel on an SNP-minor block (tcgen05 rotation only).  Same per-SNP arithmetic, identical results. */
+void jxb_set_big_solve_kernel(int variant);
 
 /* ---- file level ------------------------------------------------------------------------------------
  * lmm_reml_assoc_bed_to_tsv_f32 / lmm_reml_lmm2_assoc_bed_to_tsv_f32 / fvlmm_assoc_bed_to_tsv_f32 --

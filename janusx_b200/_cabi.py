@@ -82,6 +82,7 @@ SYMBOLS = {
     "jxb_model_stream": (_vp, [_vp]),
     "jxb_set_rotate_variant": (None, [C.c_int]),
     "jxb_set_thread_solve_min_rows": (None, [C.c_size_t]),
+    "jxb_set_big_solve_kernel": (None, [C.c_int]),
     "jxb_scan_bed_to_tsv": (C.c_int, [_vp, C.POINTER(BedScanCfg), _psz, PROGRESS_CB, _vp]),
     "jxb_format_row": (C.c_size_t, [C.c_char_p, C.c_size_t, C.c_char_p, C.c_int64, C.c_char_p, C.c_char_p,
                                     C.c_char_p, C.c_float, C.c_float, _pd, C.c_int]),

@@ -32,7 +32,8 @@ static int g_timing = 0;
 // 2 = same arithmetic with cuBLASLt slice GEMMs, 0 = FP64 DMMA GEMM, 1 = CUDA-core cross-check.
 // Chunk entry points that take arbitrary f32 genotypes always use the FP64 DMMA GEMM (or 1).
 static int g_rotate_variant = 3;
-static size_t g_thread_solve_min_rows = 32768;   // batches at least this large use the thread-per-SNP solve
+static size_t g_thread_solve_min_rows = 32768;   // batches at least this large use the large-batch solve kernels
+static int g_big_solve_kernel = 0;               // 0 = lane-per-SNP with refill (row-major block), 1 = thread-per-SNP (SNP-minor)
 
 void set_error(const std::string& msg) { g_err = msg; }
 int fail(int code, const std::string& msg) {
@@ -363,7 +364,13 @@ int scan_device_stages(jxb_model* h, const uint8_t* packed_dev, size_t bps, size
         JXB_CUDA_OK(cudaMemcpyAsync(&anym, m.flags8, sizeof anym, cudaMemcpyDeviceToHost, m.stream));
         JXB_CUDA_OK(cudaStreamSynchronize(m.stream));
         // large batches: SNP-minor output + one-thread-per-SNP solve (no shared-memory transposition)
-        const bool thread_solve = g_rotate_variant == 3 && mode != 2 && m.p <= 8 && (size_t)nk >= g_thread_solve_min_rows;
+        const bool big = mode != 2 && m.p <= 8 && (size_t)nk >= g_thread_solve_min_rows;
+        const bool lane_solve = big && g_big_solve_kernel == 0;
+        const bool thread_solve = big && !lane_solve && g_rotate_variant == 3;
+        if (lane_solve) {
+            rc = clean_rot(h);
+            if (rc) return rc;
+        }
         if (thread_solve) {
             // SNP-minor view rotT[round_up(n,32)][cap_rows]: the sample rows past n must read as zeros
             const size_t n32 = round_up(m.n, 32);
@@ -374,7 +381,13 @@ int scan_device_stages(jxb_model* h, const uint8_t* packed_dev, size_t bps, size
                                    : launch_rotate_int8_lib(m, (size_t)nk, anym != 0, m.stream);
         if (rc) return rc;
         tick(h, 4);
-        if (thread_solve) {
+        if (lane_solve) {
+            const int oc = out_cols_of(cfg, mode);
+            h->last_out_cols = oc;
+            rc = launch_solve_lane(m, m.rot, m.ldc, (size_t)nk, nullptr, to_params(cfg, mode), m.out, oc, m.evals,
+                                   m.n_kept + 1, m.stream);
+            note_launch(2);
+        } else if (thread_solve) {
             const int oc = out_cols_of(cfg, mode);
             h->last_out_cols = oc;
             rc = launch_solve_thread(m, m.rot, m.cap_rows, (size_t)nk, nullptr, to_params(cfg, mode), m.out, oc, m.evals,
@@ -443,6 +456,7 @@ uint64_t jxb_launch_count(void) { return g_launches.load(); }
 void jxb_set_timing(int on) { g_timing = on; }
 void jxb_set_rotate_variant(int variant) { g_rotate_variant = variant; }
 void jxb_set_thread_solve_min_rows(size_t rows) { g_thread_solve_min_rows = rows; }
+void jxb_set_big_solve_kernel(int variant) { g_big_solve_kernel = variant == 1 ? 1 : 0; }
 
 int jxb_model_create(int device, size_t n, size_t p, const double* s, const double* xcov, const double* y,
                      const float* u_t, jxb_model** out) {
@@ -480,7 +494,7 @@ void jxb_model_destroy(jxb_model* h) {
     Model& m = h->m;
     cudaSetDevice(m.device);
     if (m.stream) cudaStreamSynchronize(m.stream);
-    void* ptrs[] = {m.s, m.y, m.xt, m.rec, m.ut, m.g64, m.rot, m.log_table, m.out, m.evals, m.packed, m.counts, m.af, m.src_row,
+    void* ptrs[] = {m.s, m.y, m.xt, m.rec, m.ut, m.g64, m.rot, m.log_table, m.ssq, m.out, m.evals, m.packed, m.counts, m.af, m.src_row,
                     m.n_kept, m.sample_idx, m.stage_f32, m.fx_w, m.fx_py, m.fx_wx, m.fx_scal, h->missr, h->mask,
                     h->scal, m.q8, m.q8_inv_scale, m.q8_rk, m.a8, m.coef, m.flags8, m.c32, m.lt_ws, m.corr64};
     for (void* p : ptrs)

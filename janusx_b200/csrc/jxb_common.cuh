@@ -77,6 +77,7 @@ struct Model {
     double* corr64 = nullptr; size_t corr_rows = 0, ld_corr = 0;   // f64 correction terms (tcgen05 variant)
     void* tmap_a8 = nullptr; size_t tmap_a8_rows = 0; void* tmap_q8_7 = nullptr; void* tmap_q8_3 = nullptr;
     void* log_table = nullptr;                           // k3::LogTable (thread-per-SNP solve)
+    double* ssq = nullptr; size_t ssq_cap = 0;           // per-row sum of squares (lane-per-SNP solve)
     // fixed-lambda cache (A14)
     float* fx_w = nullptr; float* fx_py = nullptr; float* fx_wx = nullptr; double* fx_scal = nullptr;
     double fx_log10_lbd = 0.0; bool fx_valid = false;
@@ -111,6 +112,8 @@ int launch_solve(const Model& m, const float* g_rot, size_t ldc, size_t max_rows
                  cudaStream_t st);
 int launch_solve_thread(Model& m, const float* rotT, size_t ldr, size_t max_rows, const int32_t* n_rows_dev,
                         const SolveParams& sp, double* out, int out_cols, int32_t* evals, cudaStream_t st);
+int launch_solve_lane(Model& m, const float* rot, size_t ldc, size_t max_rows, const int32_t* n_rows_dev,
+                      const SolveParams& sp, double* out, int out_cols, int32_t* evals, int32_t* queue, cudaStream_t st);
 int launch_null_fit(const Model& m, int kind /*0 reml-null(3 out), 1 ml-null brent(2 out), 2 ml at x(1 out)*/,
                     double low, double high, int max_iter, double tol, int has_init, double init,
                     double* out_dev, cudaStream_t st);

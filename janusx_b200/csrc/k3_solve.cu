@@ -11,7 +11,10 @@ namespace jxb {
                             cudaStream_t);                                                                     \
     int k3_solve_blocks_per_sm_p##P();                                                                         \
     int k3_launch_solve_thread_p##P(const k3::ModelView&, const float*, size_t, int, const int32_t*,           \
-                                    const SolveParams&, double*, int, int32_t*, const void*, cudaStream_t);
+                                    const SolveParams&, double*, int, int32_t*, const void*, cudaStream_t);    \
+    int k3_launch_solve_lane_p##P(const k3::ModelView&, int, const float*, size_t, int, const int32_t*,        \
+                                  const SolveParams&, double*, int, int32_t*, const void*, double*, int32_t*,  \
+                                  cudaStream_t);
 JXB_DECL_P(1) JXB_DECL_P(2) JXB_DECL_P(3) JXB_DECL_P(4) JXB_DECL_P(5) JXB_DECL_P(6) JXB_DECL_P(7) JXB_DECL_P(8)
 #undef JXB_DECL_P
 
@@ -87,11 +90,8 @@ int launch_solve(const Model& m, const float* rot, size_t ldc, size_t max_rows, 
     return 0;
 }
 
-// Large-batch variant: SNP-minor rotated block, one thread per SNP (p <= 8 only).
-int launch_solve_thread(Model& m, const float* rotT, size_t ldr, size_t max_rows, const int32_t* n_rows_dev,
-                        const SolveParams& sp, double* out, int out_cols, int32_t* evals, cudaStream_t st) {
-    if (max_rows == 0) return 0;
-    if (m.p < 1 || m.p > 8) return fail(-2, "thread-per-SNP solve supports 1..8 covariate columns");
+// 128-bucket table of the table-driven log (k3_solve.cuh table_log), built once per model
+static int ensure_log_table(Model& m, cudaStream_t st) {
     if (!m.log_table) {
         // 128-bucket table: c = 1 + (i + 0.5)/128, 1/c rounded, ln c split hi/lo (long double on the host)
         LogTable h;
@@ -107,12 +107,45 @@ int launch_solve_thread(Model& m, const float* rotT, size_t ldr, size_t max_rows
         JXB_CUDA_OK(cudaMemcpyAsync(m.log_table, &h, sizeof(LogTable), cudaMemcpyHostToDevice, st));
         JXB_CUDA_OK(cudaStreamSynchronize(st));
     }
+    return 0;
+}
+
+// Large-batch variant: SNP-minor rotated block, one thread per SNP (p <= 8 only).
+int launch_solve_thread(Model& m, const float* rotT, size_t ldr, size_t max_rows, const int32_t* n_rows_dev,
+                        const SolveParams& sp, double* out, int out_cols, int32_t* evals, cudaStream_t st) {
+    if (max_rows == 0) return 0;
+    if (m.p < 1 || m.p > 8) return fail(-2, "thread-per-SNP solve supports 1..8 covariate columns");
+    { int rc = ensure_log_table(m, st); if (rc) return rc; }
     const ModelView mv = view_of(m);
 #define T_STATIC(P) k3_launch_solve_thread_p##P(mv, rotT, ldr, (int)max_rows, n_rows_dev, sp, out, out_cols, evals, m.log_table, st)
 #define T_DYN() (void)0
     JXB_DISPATCH_P((int)m.p, T_STATIC, T_DYN)
 #undef T_STATIC
 #undef T_DYN
+    JXB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// Large-batch variant, row-major rotated block: lane-per-SNP with refill (p <= 8 only).
+int launch_solve_lane(Model& m, const float* rot, size_t ldc, size_t max_rows, const int32_t* n_rows_dev,
+                      const SolveParams& sp, double* out, int out_cols, int32_t* evals, int32_t* queue, cudaStream_t st) {
+    if (max_rows == 0) return 0;
+    if (m.p < 1 || m.p > 8) return fail(-2, "lane-per-SNP solve supports 1..8 covariate columns");
+    { int rc = ensure_log_table(m, st); if (rc) return rc; }
+    if (m.ssq_cap < max_rows) {
+        JXB_CUDA_OK(cudaStreamSynchronize(st));
+        if (m.ssq) cudaFree(m.ssq);
+        m.ssq = nullptr;
+        JXB_CUDA_OK(cudaMalloc((void**)&m.ssq, std::max(max_rows, m.cap_rows) * sizeof(double)));
+        m.ssq_cap = std::max(max_rows, m.cap_rows);
+    }
+    const ModelView mv = view_of(m);
+    const int sms = sm_count(m.device);
+#define L_STATIC(P) k3_launch_solve_lane_p##P(mv, sms, rot, ldc, (int)max_rows, n_rows_dev, sp, out, out_cols, evals, m.log_table, m.ssq, queue, st)
+#define L_DYN() (void)0
+    JXB_DISPATCH_P((int)m.p, L_STATIC, L_DYN)
+#undef L_STATIC
+#undef L_DYN
     JXB_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -404,6 +404,11 @@ def set_thread_solve_min_rows(rows: int) -> None:
     lib().jxb_set_thread_solve_min_rows(int(rows))
 
 
+def set_big_solve_kernel(variant: int) -> None:
+    """Large-batch solve kernel: 0 = lane-per-SNP with refill (default), 1 = thread-per-SNP on an SNP-minor block."""
+    lib().jxb_set_big_solve_kernel(int(variant))
+
+
 def clear_model_cache() -> None:
     while _CACHE:
         _, m = _CACHE.popitem()

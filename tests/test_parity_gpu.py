@@ -444,10 +444,11 @@ def test_int8_sliced_rotation_variant(jx, oracle):
         jx.set_rotate_variant(3)
 
 
+@pytest.mark.parametrize("big_kernel", [0, 1])
 @pytest.mark.parametrize("mode", ["lmm", "lmm2"])
-def test_thread_per_snp_solve_kernel(jx, oracle, mode):
-    """The large-batch path (tcgen05 rotation writing an SNP-minor block + one thread per SNP with the
-    table-driven log) must satisfy the same gates as the warp kernel."""
+def test_thread_per_snp_solve_kernel(jx, oracle, mode, big_kernel):
+    """The large-batch solve kernels -- 0: lane-per-SNP with refill on the row-major block (default), 1: one thread per
+    SNP on an SNP-minor block -- must satisfy the same gates as the warp kernel, evaluation for evaluation."""
     case = make_problem(n=450, m=500, q=3, seed=411, missing_rate=0.02)
     nm = null_model(oracle, case)
     n = case.n
@@ -457,10 +458,13 @@ def test_thread_per_snp_solve_kernel(jx, oracle, mode):
     mdl = jx.DeviceModel(case.s, nm["xcov"], nm["y"], nm["ut"])
     try:
         jx.set_thread_solve_min_rows(1)
+        jx.set_big_solve_kernel(big_kernel)
         if mode == "lmm":
-            want = oracle.lmm_reml_chunk_from_snp_f32(case.s, nm["xcov"], nm["y"], nm["low"], nm["high"], g, nm["ut"], 30, 1e-2)
+            want, ev_o = oracle.lmm_reml_chunk_f32(case.s, nm["xcov"], nm["y"], nm["low"], nm["high"],
+                                                   oracle.rotate_block(g, nm["ut"]), 30, 1e-2, return_evals=True)
             k, _, _, out, ev = mdl.scan_packed(case.packed, n, low=nm["low"], high=nm["high"], return_evals=True)
             assert_results_close(out, want)
+            assert np.array_equal(ev, ev_o)
         else:
             _, mlnull = oracle.lmm_ml_null_brent(case.s, nm["xcov"], nm["y"], nm["low"], nm["high"], 30, 1e-2)
             want = oracle.lmm_reml_lmm2_chunk_from_snp_f32(case.s, nm["xcov"], nm["y"], nm["low"], nm["high"], g, nm["ut"], mlnull, 30, 1e-2)
@@ -475,6 +479,7 @@ def test_thread_per_snp_solve_kernel(jx, oracle, mode):
         assert_results_close(out_w, want, cols_p=((2, 5) if mode == "lmm2" else (2,)))
     finally:
         jx.set_thread_solve_min_rows(32768)
+        jx.set_big_solve_kernel(0)
 
 
 def test_full_size_n20000_parity_sample(jx, oracle):
@@ -516,7 +521,11 @@ def test_full_size_n20000_parity_sample(jx, oracle):
     kw = dict(mode="lmm2", low=lo, high=hi, init=l10, nullml=nullml)
     try:
         jx.set_thread_solve_min_rows(1)
-        k1, af1, ms1, out1 = mdl.scan_packed(packed, n, **kw)          # tcgen05 + thread kernel (bench path)
+        k1, af1, ms1, out1 = mdl.scan_packed(packed, n, **kw)          # tcgen05 + lane kernel (bench path)
+        jx.set_big_solve_kernel(1)
+        _, _, _, out1b = mdl.scan_packed(packed, n, **kw)              # tcgen05 + thread kernel (SNP-minor block)
+        jx.set_big_solve_kernel(0)
+        assert np.array_equal(out1, out1b, equal_nan=True)             # same per-SNP arithmetic, bit for bit
         jx.set_thread_solve_min_rows(1 << 30)
         k2, _, _, out2 = mdl.scan_packed(packed, n, **kw)                # tcgen05 + warp kernel
         jx.set_rotate_variant(0)
