@@ -173,6 +173,36 @@ def test_k3_covariate_counts(jx, oracle, p_cov):
     assert_results_close(got2, want2, cols_p=(2, 5), cols_lambda=(3,))
 
 
+@pytest.mark.parametrize("p_cov", [1, 5, 8])
+def test_big_solve_kernels_covariate_counts(jx, oracle, p_cov):
+    """Large-batch solve kernels (lane-per-SNP default, thread-per-SNP) for other covariate counts than the bench's 4,
+    incl. p >= 5 where they run at 3 CTAs/SM; -lmm2 through the packed scan, evaluation counts included."""
+    case = make_problem(n=180, m=96, q=p_cov - 1, seed=60 + p_cov, missing_rate=0.02)
+    nm = null_model(oracle, case)
+    n = case.n
+    keep, af, _, _ = oracle.count_qc_block(case.packed, n, None, 0.02, 0.05, 1.0)
+    idx = np.nonzero(keep)[0]
+    g = oracle.decode_centered_block(case.packed, n, af[idx], row_indices=idx)
+    _, mlnull = oracle.lmm_ml_null_brent(case.s, nm["xcov"], nm["y"], nm["low"], nm["high"], 30, 1e-2)
+    want, ev_o = oracle.lmm_reml_lmm2_chunk_f32(case.s, nm["xcov"], nm["y"], nm["low"], nm["high"],
+                                                oracle.rotate_block(g, nm["ut"]), mlnull, 30, 1e-2, return_evals=True)
+    mdl = jx.DeviceModel(case.s, nm["xcov"], nm["y"], nm["ut"])
+    outs = []
+    try:
+        jx.set_thread_solve_min_rows(1)
+        for variant in (0, 1):
+            jx.set_big_solve_kernel(variant)
+            k, _, _, out, ev = mdl.scan_packed(case.packed, n, mode="lmm2", low=nm["low"], high=nm["high"], nullml=mlnull,
+                                               return_evals=True)
+            assert np.array_equal(k, keep) and np.array_equal(ev, ev_o)
+            assert_results_close(out, want, cols_p=(2, 5), cols_lambda=(3,))
+            outs.append(out)
+    finally:
+        jx.set_thread_solve_min_rows(32768)
+        jx.set_big_solve_kernel(0)
+    assert np.array_equal(outs[0], outs[1], equal_nan=True)
+
+
 def test_end_to_end_from_snp_and_packed(jx, oracle):
     case = make_problem(n=400, m=600, q=3, seed=77, missing_rate=0.02)
     nm = null_model(oracle, case)
