@@ -153,3 +153,29 @@ def test_lmm_lm_null_lrt_decision_host_logic():
         jxrs.gwas_lmm_lm_null_lrt_decision(y, x, 0.0, alpha=1.5)
     with pytest.raises(RuntimeError, match="insufficient samples"):
         jxrs.gwas_lmm_lm_null_lrt_decision(y[:3], x[:3], 0.0)
+
+
+def test_cli_argument_rules_and_vcf_cache(tmp_path, monkeypatch):
+    """Host-side CLI logic that needs no GPU: flag validation and the VCF -> PLINK cache (rebuilt only when stale)."""
+    from janusx_b200 import gwas, jxrs
+    with pytest.raises(SystemExit):
+        gwas.parse_args(["-p", "pheno.tsv", "-lmm"])                              # neither -bfile nor -vcf
+    with pytest.raises(SystemExit):
+        gwas.parse_args(["-bfile", "a", "-vcf", "b.vcf", "-p", "pheno.tsv", "-lmm"])  # both
+    with pytest.raises(SystemExit):
+        gwas.parse_args(["-bfile", "a", "-p", "pheno.tsv"])                       # no model selected
+    a = gwas.parse_args(["-vcf", "x.vcf.gz", "-p", "p.tsv", "-lmm2", "-maf", "0.05", "-snps-only"])
+    assert a.vcf == "x.vcf.gz" and a.lmm2 and not a.lmm and a.maf == 0.05 and a.snps_only and a.grm == "1"
+    vcf = tmp_path / "toy.vcf"
+    vcf.write_text("#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\ta\tb\n1\t10\trs1\tA\tG\t.\t.\t.\tGT\t0/1\t1/1\n")
+    calls = []
+    real = jxrs.vcf_to_plink
+    monkeypatch.setattr(jxrs, "vcf_to_plink", lambda *args: (calls.append(args), real(*args))[1])
+    prefix = gwas._vcf_cache(str(vcf), str(tmp_path), False)
+    assert prefix.endswith("~toy.snp0") and len(calls) == 1 and Path(prefix + ".bed").read_bytes() == b"\x6c\x1b\x01\x0e"
+    assert gwas._vcf_cache(str(vcf), str(tmp_path), False) == prefix and len(calls) == 1      # fresh: reused
+    import os
+    os.utime(vcf, (os.path.getmtime(prefix + ".bed") + 10,) * 2)
+    gwas._vcf_cache(str(vcf), str(tmp_path), False)
+    assert len(calls) == 2                                                                     # stale: rebuilt
+    assert jxrs.default_device_batch(20000) == 151552 and jxrs.default_device_batch(50000) == 75776
