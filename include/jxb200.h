@@ -133,6 +133,14 @@ int jxb_scan_fetch(jxb_model* m, size_t rows, int out_cols, uint8_t* keep_host, 
 int jxb_decode_packed(jxb_model* m, const uint8_t* packed_host, size_t bytes_per_snp, size_t rows, size_t n_full,
                       const int64_t* sample_idx_host, const jxb_qc_cfg* qc, int32_t* counts_host, float* af_host,
                       float* miss_rate_host, float* g_host, size_t* n_kept_host);
+/* Decode with caller-supplied row decisions: keep_host u8[rows] selects the rows, af_host f32[rows] is the allele
+ * frequency whose double is the imputed dosage.  Serves BedChunkReader.next_chunk_prepared (route B,
+ * src/io/gfreader.rs:3580-3700), whose QC arithmetic (f64 rates, src/io/gfcore.rs:405-480) differs from the unified
+ * scan's f32 expressions and is therefore evaluated by the caller from the exact integer counts of jxb_decode_packed.
+ * g_host f32[n_kept, n] centred rows in source order. */
+int jxb_decode_packed_prepared(jxb_model* m, const uint8_t* packed_host, size_t bps, size_t rows, size_t n_full,
+                               const int64_t* sample_idx_host, const uint8_t* keep_host, const float* af_host,
+                               int genetic_model, float* g_host, size_t* n_kept);
 
 /* Per-stage device timers of the last jxb_scan_packed* call, milliseconds:
  * [0]=count+qc+compact [1]=decode [2]=rotate [3]=solve [4]=h2d [5]=d2h.  (The reference's

@@ -77,6 +77,8 @@ SYMBOLS = {
     "jxb_scan_fetch": (C.c_int, [_vp, C.c_size_t, C.c_int, _vp, _vp, _vp, _vp, _vp, _psz]),
     "jxb_decode_packed": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_size_t, _vp, C.POINTER(QcCfg), _vp, _vp,
                                     _vp, _vp, _psz]),
+    "jxb_decode_packed_prepared": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_size_t, _vp, _vp, _vp, C.c_int, _vp,
+                                             _psz]),
     "jxb_set_timing": (None, [C.c_int]),
     "jxb_last_stage_ms": (C.c_int, [_vp, _pf]),
     "jxb_model_stream": (_vp, [_vp]),

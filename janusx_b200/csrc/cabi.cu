@@ -766,6 +766,53 @@ int jxb_decode_packed(jxb_model* h, const uint8_t* packed, size_t bps, size_t ro
     return 0;
 }
 
+int jxb_decode_packed_prepared(jxb_model* h, const uint8_t* packed, size_t bps, size_t rows, size_t n_full,
+                               const int64_t* sidx, const uint8_t* keep_host, const float* af_host, int genetic_model,
+                               float* g_host, size_t* n_kept_host) {
+    if (!h || !packed || !keep_host || !af_host || !g_host) return fail(-2, "null argument");
+    if (bps != (n_full + 3) / 4) return fail(-2, "bytes_per_snp must equal ceil(n_full/4)");
+    if (!sidx && n_full != h->m.n) return fail(-2, "sample_ids length != expected sample count");
+    if (genetic_model < 0 || genetic_model > 3) return fail(-2, "model must be one of: add, dom, rec, het");
+    if (rows == 0) { if (n_kept_host) *n_kept_host = 0; return 0; }
+    Model& m = h->m;
+    int rc = ensure_capacity(h, rows, bps, false);
+    if (rc) return rc;
+    const size_t n = m.n;
+    JXB_CUDA_OK(cudaMemcpyAsync(m.packed, packed, rows * bps, cudaMemcpyHostToDevice, m.stream));
+    const int64_t* sidx_dev = nullptr;
+    if (sidx) {
+        rc = ensure_sample_idx(m, sidx, n, false);
+        if (rc) return rc;
+        sidx_dev = m.sample_idx;
+    }
+    // genotype counts feed the closed-form row mean; the caller's keep flags and allele frequencies replace the QC
+    rc = launch_count_qc(m, m.packed, bps, rows, n_full, sidx_dev, n, 0.0f, 1.0f, 0.0f, m.counts, m.af, h->missr, m.stream);
+    note_launch(1);
+    if (rc) return rc;
+    JXB_CUDA_OK(cudaMemcpyAsync(h->mask, keep_host, rows, cudaMemcpyHostToDevice, m.stream));
+    JXB_CUDA_OK(cudaMemcpyAsync(m.af, af_host, rows * sizeof(float), cudaMemcpyHostToDevice, m.stream));
+    apply_mask_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, m.stream>>>(m.counts, h->mask, (int)rows);
+    note_launch(1);
+    rc = launch_compact(m.counts, rows, m.src_row, m.n_kept, m.stream);
+    note_launch(1);
+    if (rc) return rc;
+    int32_t nk = 0;
+    JXB_CUDA_OK(cudaMemcpyAsync(&nk, m.n_kept, sizeof nk, cudaMemcpyDeviceToHost, m.stream));
+    JXB_CUDA_OK(cudaStreamSynchronize(m.stream));
+    if (n_kept_host) *n_kept_host = (size_t)nk;
+    if (nk > 0) {
+        rc = ensure_stage_f32(m, (size_t)nk * n);
+        if (rc) return rc;
+        rc = launch_decode_center(m.packed, bps, m.src_row, m.n_kept, rows, n_full, sidx_dev, n, m.af, m.counts,
+                                  genetic_model, nullptr, 0, m.stage_f32, n, m.stream);
+        note_launch(1);
+        if (rc) return rc;
+        JXB_CUDA_OK(cudaMemcpyAsync(g_host, m.stage_f32, (size_t)nk * n * sizeof(float), cudaMemcpyDeviceToHost, m.stream));
+        JXB_CUDA_OK(cudaStreamSynchronize(m.stream));
+    }
+    return 0;
+}
+
 int jxb_last_stage_ms(jxb_model* h, float ms6[6]) {
     if (!h) return fail(-2, "model is null");
     for (int i = 0; i < 6; ++i) ms6[i] = h->stage_ms[i];

@@ -1,0 +1,229 @@
+"""BedChunkReader: the prepared-chunk source of the reference's route "B" (several models on one trait share decoded
+chunks: SURVEY 3.2), device-backed.
+
+Mirrors `BedChunkReader` of src/io/gfreader.rs:3138-3760 for the exact-LMM path: constructor arguments, `n_samples`,
+`n_snps`, `sample_ids` and `next_chunk_prepared(chunk_size, coding, snps_only) -> (f32[m, n] centred, sites, af, miss)`.
+The per-row QC of this route is NOT the unified scan's f32 arithmetic: it runs in f64 on the genotype counts
+(process_snp_row_with_precomputed_counts_impl, src/io/gfcore.rs:405-480).  The counts are exact integers, so they come
+from the device (jxb_decode_packed), the handful of f64 expressions per row is evaluated here exactly as the reference
+writes them, and the decode / impute / centre of the kept rows runs on the device (jxb_decode_packed_prepared).
+Not built: raw `next_chunk`, bim_range / snp_sites / chr_keys / bp_min / bp_max / ranges selectors, the windowed mmap,
+non-additive codings (their value map applies a 1e-6 tolerance to the imputed dosage, src/io/gfreader.rs:3161-3186).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from ._cabi import check, lib, ptr, require_gpu
+from .jxrs import DeviceModel, SiteInfo
+
+
+class ChunkSite(SiteInfo):
+    """chrom / pos / snp / ref_allele / alt_allele (the Py-exposed SiteInfo, src/io/gfreader.rs:33-47)."""
+    __slots__ = ("snp",)
+
+    def __init__(self, chrom, pos, snp, ref_allele, alt_allele):
+        super().__init__(chrom, pos, ref_allele, alt_allele)
+        self.snp = str(snp)
+
+
+def _simple_allele(a: str) -> bool:
+    a = a.strip()
+    return len(a) == 1 and a.upper() in "ACGT"
+
+
+def prepared_row_decisions(missing, het, hom_alt, n: int, maf_thr: float, miss_thr: float, het_thr: float):
+    """The f64 QC of route B on integer genotype counts (src/io/gfcore.rs:405-480, preserve_alt_orientation = true,
+    fill_missing = true) -> (keep bool[m], imputed f32[m]).  Thresholds are f32 like the reference's fields."""
+    missing = np.asarray(missing, dtype=np.int64)
+    het = np.asarray(het, dtype=np.int64)
+    hom = np.asarray(hom_alt, dtype=np.int64)
+    maf_t, miss_t, het_t = np.float32(maf_thr), np.float32(miss_thr), np.float32(het_thr)
+    non_missing = n - missing
+    alt_sum = (het + 2 * hom).astype(np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        missing_rate = (1.0 - non_missing.astype(np.float64) / float(n)).astype(np.float32)
+        keep = ~(missing_rate > miss_t)
+        empty = non_missing == 0
+        keep &= ~(empty & (maf_t > 0))
+        if het_t < np.float32(1.0):                                   # apply_het_filter = het < 1.0
+            het_rate = het.astype(np.float64) / non_missing.astype(np.float64)
+            keep &= ~(~empty & (het_rate > np.float64(het_t)))
+        alt_freq = alt_sum / (2.0 * non_missing.astype(np.float64))
+        maf = np.minimum(alt_freq, 1.0 - alt_freq).astype(np.float32)
+        keep &= ~(~empty & (maf < maf_t))
+        imputed = (alt_sum / non_missing.astype(np.float64)).astype(np.float32)
+    imputed = np.where(empty, np.float32(0.0), imputed).astype(np.float32)   # all-missing rows are filled with 0
+    return keep, imputed
+
+
+class BedChunkReader:
+    def __init__(self, prefix, maf_threshold=None, max_missing_rate=None, fill_missing=None, snp_range=None,
+                 snp_indices=None, bim_range=None, snp_sites=None, sample_ids=None, sample_indices=None,
+                 mmap_window_mb=None, chr_keys=None, bp_min=None, bp_max=None, ranges=None, model=None,
+                 het_threshold=None, device: int = 0):
+        require_gpu()
+        self.maf = 0.0 if maf_threshold is None else float(maf_threshold)
+        self.miss = 1.0 if max_missing_rate is None else float(max_missing_rate)
+        if fill_missing is not None and not fill_missing:
+            raise NotImplementedError("fill_missing=False is not built (the LMM path always imputes)")
+        model_key = (model or "add").lower()
+        if model_key not in ("add", "dom", "rec", "het"):
+            raise ValueError("model must be one of: add, dom, rec, het")
+        self.het = 1.0 if het_threshold is None else float(het_threshold)
+        if not (0.0 <= self.het <= 1.0):
+            raise ValueError("het_threshold must be within [0, 1.0]")
+        for name, v in (("bim_range", bim_range), ("snp_sites", snp_sites), ("mmap_window_mb", mmap_window_mb),
+                        ("chr_keys", chr_keys), ("bp_min", bp_min), ("bp_max", bp_max), ("ranges", ranges)):
+            if v is not None:
+                raise NotImplementedError(f"BedChunkReader({name}=...) is not built in janusx_b200")
+        self.prefix = str(prefix)
+        with open(self.prefix + ".fam") as fh:
+            fam = [line.split()[1] for line in fh if line.strip()]
+        if not fam:
+            raise RuntimeError("no samples in PLINK FAM")
+        self._n_full = len(fam)
+        # build_sample_selection, src/io/gfreader.rs:75-123
+        if sample_ids is not None and sample_indices is not None:
+            raise RuntimeError("Provide only one of sample_ids or sample_indices")
+        if sample_ids is not None:
+            ids = [str(s) for s in sample_ids]
+            if not ids:
+                raise RuntimeError("sample_ids is empty")
+            pos = {sid: i for i, sid in enumerate(fam)}
+            idx, seen = [], set()
+            for sid in ids:
+                if sid not in pos:
+                    raise RuntimeError(f"sample id not found: {sid}")
+                if pos[sid] in seen:
+                    raise RuntimeError(f"duplicate sample id: {sid}")
+                seen.add(pos[sid])
+                idx.append(pos[sid])
+        elif sample_indices is not None:
+            idx = [int(i) for i in sample_indices]
+            if not idx:
+                raise RuntimeError("sample_indices is empty")
+            seen = set()
+            for i in idx:
+                if i < 0 or i >= len(fam):
+                    raise RuntimeError(f"sample index out of range: {i}")
+                if i in seen:
+                    raise RuntimeError(f"duplicate sample index: {i}")
+                seen.add(i)
+            ids = [fam[i] for i in idx]
+        else:
+            idx, ids = list(range(len(fam))), list(fam)
+        self._sidx = np.asarray(idx, dtype=np.int64)
+        self._ids = ids
+        self._identity = len(idx) == len(fam) and idx == list(range(len(fam)))
+        # sites + packed payload
+        self._sites: List[ChunkSite] = []
+        with open(self.prefix + ".bim") as fh:
+            for ln, line in enumerate(fh, 1):
+                tok = line.split()
+                if len(tok) < 6:
+                    raise RuntimeError(f"Malformed BIM line at {self.prefix}.bim:{ln}: {line.rstrip()}")
+                try:
+                    p = int(tok[3])
+                    p = p if -(1 << 31) <= p < (1 << 31) else 0
+                except ValueError:
+                    p = 0
+                self._sites.append(ChunkSite(tok[0], p, tok[1], tok[4], tok[5]))
+        bps = (self._n_full + 3) // 4
+        raw = np.memmap(self.prefix + ".bed", dtype=np.uint8, mode="r")
+        if raw.shape[0] < 3 or bytes(raw[:3]) != b"\x6c\x1b\x01":
+            raise RuntimeError("only SNP-major BED supported")
+        if (raw.shape[0] - 3) % bps != 0 or (raw.shape[0] - 3) // bps != len(self._sites):
+            raise RuntimeError("BED payload does not match the FAM/BIM dimensions")
+        self._packed = raw[3:].reshape(len(self._sites), bps)
+        # build_snp_indices, src/io/gfreader.rs:125-172 (snp_range / snp_indices only)
+        if snp_range is not None and snp_indices is not None:
+            raise RuntimeError("Provide only one of snp_range, snp_indices, bim_range, or snp_sites")
+        self._snp_indices: Optional[np.ndarray] = None
+        if snp_range is not None:
+            start, end = int(snp_range[0]), int(snp_range[1])
+            if start >= end or end > len(self._sites):
+                raise RuntimeError(f"invalid snp_range: ({start}, {end})")
+            self._snp_indices = np.arange(start, end, dtype=np.int64)
+        elif snp_indices is not None:
+            si = np.asarray(list(snp_indices), dtype=np.int64)
+            if si.size == 0:
+                raise RuntimeError("snp_indices is empty")
+            if si.min() < 0 or si.max() >= len(self._sites):
+                raise RuntimeError(f"snp index out of range: {int(si.max() if si.max() >= len(self._sites) else si.min())}")
+            if np.unique(si).size != si.size:
+                raise RuntimeError("duplicate snp index")
+            self._snp_indices = si
+        self._cursor = 0
+        n = len(idx)
+        self._dev = DeviceModel(np.ones(n), np.ones((n, 1)), np.zeros(n), device=device)   # decode workspace only
+
+    @property
+    def n_samples(self) -> int:
+        return len(self._ids)
+
+    @property
+    def n_snps(self) -> int:
+        return len(self._sites) if self._snp_indices is None else int(self._snp_indices.shape[0])
+
+    @property
+    def sample_ids(self) -> List[str]:
+        return list(self._ids)
+
+    def _source_rows(self, count: int) -> np.ndarray:
+        if self._snp_indices is None:
+            rows = np.arange(self._cursor, min(self._cursor + count, len(self._sites)), dtype=np.int64)
+        else:
+            rows = self._snp_indices[self._cursor:self._cursor + count]
+        self._cursor += int(rows.shape[0])
+        return rows
+
+    def next_chunk_prepared(self, chunk_size: int, coding: Optional[str] = None, snps_only: bool = False):
+        """-> None at the end, else (geno_centered f32[m, n], sites, af f32[m], miss f32[m]); m <= chunk_size rows that
+        passed the QC, in BED order (the reference keeps reading until the chunk is full)."""
+        if chunk_size == 0:
+            raise ValueError("chunk_size must be > 0")
+        coding_key = (coding or "add").strip().lower()
+        if coding_key not in ("add", "dom", "rec", "het"):
+            raise ValueError("coding must be one of: add, dom, rec, het")
+        if coding_key != "add":
+            raise NotImplementedError("next_chunk_prepared: only the additive coding is built in janusx_b200")
+        n = self.n_samples
+        sidx = None if self._identity else self._sidx
+        blocks, sites, afs, misses, m = [], [], [], [], 0
+        while m < chunk_size and self._cursor < self.n_snps:
+            rows = self._source_rows(chunk_size - m)
+            packed = np.ascontiguousarray(self._packed[rows])
+            counts, _, _, _ = self._dev.decode_packed(packed, self._n_full, sidx, 0.0, 1.0, 0.0, want_g=False)
+            keep, imputed = prepared_row_decisions(counts[:, 0], counts[:, 1], counts[:, 2], n, self.maf, self.miss, self.het)
+            if snps_only:
+                keep &= np.array([_simple_allele(self._sites[int(r)].ref_allele) and _simple_allele(self._sites[int(r)].alt_allele)
+                                  for r in rows], dtype=bool)
+            nk = int(keep.sum())
+            if nk == 0:
+                continue
+            g = np.empty((nk, n), dtype=np.float32)
+            got = C.c_size_t()
+            keep_u8 = np.ascontiguousarray(keep, dtype=np.uint8)
+            af_half = np.ascontiguousarray(imputed * np.float32(0.5), dtype=np.float32)   # f32(2 * af) == imputed, exactly
+            check(lib().jxb_decode_packed_prepared(self._dev.handle, ptr(packed), packed.shape[1], packed.shape[0],
+                                                   self._n_full, ptr(sidx), ptr(keep_u8), ptr(af_half), 0, ptr(g),
+                                                   C.byref(got)))
+            if got.value != nk:
+                raise RuntimeError("internal error: device kept-row count differs from the host decisions")
+            k = np.nonzero(keep)[0]
+            miss_cnt = counts[k, 0].astype(np.int64)
+            # coded_mean = (sum of the filled row in f64 / n) as f32; the sum is exact (gfreader.rs:3667-3680)
+            total = (counts[k, 1] + 2 * counts[k, 2]).astype(np.float64) + miss_cnt.astype(np.float64) * imputed[k].astype(np.float64)
+            coded_mean = (total / float(n)).astype(np.float32)
+            blocks.append(g)
+            sites.extend(self._sites[int(rows[i])] for i in k)
+            afs.append(coded_mean * np.float32(0.5))
+            misses.append(miss_cnt.astype(np.float32))
+            m += nk
+        if m == 0:
+            return None
+        return np.concatenate(blocks), sites, np.concatenate(afs), np.concatenate(misses)

@@ -1117,3 +1117,11 @@ def gwas_lmm_lm_null_lrt_decision(y, x_cov, lmm_ml0, alpha=0.05, boundary_mixtur
         pval = 1.0
     pval = min(max(pval, 2.2250738585072014e-308), 1.0)
     return bool(pval >= alpha), float(stat), float(pval), float(lm_ml0)
+
+
+def __getattr__(name):
+    # `janusx.janusx.BedChunkReader` lives in gfreader.py (which imports this module): resolve it lazily
+    if name == "BedChunkReader":
+        from .gfreader import BedChunkReader
+        return BedChunkReader
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

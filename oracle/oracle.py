@@ -371,6 +371,58 @@ def format_row(chrom: str, pos: int, snp: str, a0: str, a1: str, af: float, miss
 
 
 # ------------------------------------------------------------------------------------------
+# Route B: BedChunkReader.next_chunk_prepared rows (additive coding) -- numpy restatement
+# ------------------------------------------------------------------------------------------
+def bed_chunk_prepared_rows(packed, n_samples, sample_idx=None, maf_thr=0.0, miss_thr=1.0, het_thr=1.0):
+    """src/io/gfreader.rs:3580-3700 + process_snp_row_with_precomputed_counts_impl (src/io/gfcore.rs:405-480,
+    preserve_alt_orientation=true, fill_missing=true), row by row exactly as written there: decode to f32 dosages
+    (-9 = missing), f64 QC, impute with (alt_sum / non_missing) as f32, centre with (f64 sum / n) as f32.
+    -> (keep bool[m], g f32[kept, n], af f32[kept], miss f32[kept])."""
+    packed = np.ascontiguousarray(packed, dtype=np.uint8)
+    idx = np.arange(n_samples) if sample_idx is None else np.asarray(sample_idx, dtype=np.int64)
+    n = idx.shape[0]
+    lut = np.array([0.0, -9.0, 1.0, 2.0], dtype=np.float32)
+    maf_t, miss_t, het_t = np.float32(maf_thr), np.float32(miss_thr), np.float32(het_thr)
+    apply_het = het_t < np.float32(1.0)
+    keep = np.zeros(packed.shape[0], dtype=bool)
+    rows, afs, misses = [], [], []
+    for r in range(packed.shape[0]):
+        codes = (packed[r, idx >> 2] >> (2 * (idx & 3)).astype(np.uint8)) & 3
+        row = lut[codes].copy()
+        obs = row >= 0.0
+        non_missing = int(obs.sum())
+        alt_sum = 0.0
+        for v in row[obs]:                       # scan_snp_row_counts: sequential f64 sum
+            alt_sum += float(v)
+        het_count = int((np.abs(row[obs] - np.float32(1.0)) < np.float32(1e-6)).sum())
+        missing_rate = np.float32(1.0 - non_missing / float(n))
+        missing_count = n - non_missing
+        if missing_rate > miss_t:
+            continue
+        if non_missing == 0:
+            if maf_t > 0:
+                continue
+            row[:] = 0.0
+        else:
+            if apply_het and het_count / float(non_missing) > float(het_t):
+                continue
+            alt_freq = alt_sum / (2.0 * non_missing)
+            if np.float32(min(alt_freq, 1.0 - alt_freq)) < maf_t:
+                continue
+            row[~obs] = np.float32(alt_sum / non_missing)
+        total = 0.0
+        for v in row:
+            total += float(v)
+        coded_mean = np.float32(total / float(n))
+        keep[r] = True
+        rows.append((row - coded_mean).astype(np.float32))
+        afs.append(np.float32(coded_mean * np.float32(0.5)))
+        misses.append(np.float32(missing_count))
+    g = np.array(rows, dtype=np.float32).reshape(len(rows), n)
+    return keep, g, np.array(afs, dtype=np.float32), np.array(misses, dtype=np.float32)
+
+
+# ------------------------------------------------------------------------------------------
 # N1: centred additive GRM (SURVEY 8f) -- numpy restatement, f64 contraction
 # ------------------------------------------------------------------------------------------
 def grm_packed_f64(packed, n_samples, row_flip, row_maf, sample_indices=None, method=1, mu_grid_bits=None):

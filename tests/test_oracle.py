@@ -210,3 +210,31 @@ def test_bed_scan_composition(oracle, tmp_path):
     oracle.scan_bed_to_tsv(prefix, str(out2), case.s, nm["xcov"], nm["y"], nm["ut"], 0.02, 0.05, 1.0,
                            low=nm["low"], high=nm["high"], rotate_block_rows=512)
     assert out.read_bytes() == out2.read_bytes()
+
+
+def test_route_b_row_decisions_match_restatement(oracle):
+    """BedChunkReader.next_chunk_prepared (route B): the host-side f64 QC of janusx_b200/gfreader.py on integer counts
+    against the row-by-row restatement of src/io/gfcore.rs:405-480 + src/io/gfreader.rs:3660-3681."""
+    from janusx_b200 import synth
+    from janusx_b200.gfreader import prepared_row_decisions
+    n_full, m = 123, 400
+    packed, _ = synth.draw_genotypes(m, n_full, seed=9, missing_rate=0.08)
+    packed[3] = 0b01010101        # all missing
+    packed[4] = 0                 # monomorphic
+    sidx = np.array(sorted(np.random.default_rng(0).choice(n_full, size=77, replace=False)), dtype=np.int64)
+    for idx in (None, sidx):
+        sel = np.arange(n_full) if idx is None else idx
+        codes = (packed[:, sel >> 2] >> (2 * (sel & 3)).astype(np.uint8)) & 3
+        het, hom, mis = (codes == 2).sum(1), (codes == 3).sum(1), (codes == 1).sum(1)
+        for thr in ((0.0, 1.0, 1.0), (0.05, 0.1, 1.0), (0.02, 0.05, 0.4), (0.1, 0.02, 0.0)):
+            keep_o, g, af, miss = oracle.bed_chunk_prepared_rows(packed, n_full, idx, *thr)
+            keep, imputed = prepared_row_decisions(mis, het, hom, sel.shape[0], *thr)
+            assert np.array_equal(keep, keep_o), thr
+            k = np.nonzero(keep)[0]
+            total = (het[k] + 2 * hom[k]).astype(np.float64) + mis[k].astype(np.float64) * imputed[k].astype(np.float64)
+            coded_mean = (total / float(sel.shape[0])).astype(np.float32)
+            assert np.array_equal((coded_mean * np.float32(0.5)).view(np.uint32), af.view(np.uint32))
+            assert np.array_equal(miss, mis[k].astype(np.float32))
+            # the restated rows are centred: f32 row sums vanish to rounding
+            if k.size:
+                assert np.abs(g.astype(np.float64).sum(axis=1)).max() < 1e-3

@@ -1,0 +1,117 @@
+"""Route B: BedChunkReader.next_chunk_prepared -> LMM.gwas / LMM2.gwas / FvLMM.gwas -> GwasAssocTsvWriter,
+the chain the reference runs when several models share one trait's decoded chunks.  The reader's rows must equal the
+row-by-row restatement of src/io/gfreader.rs:3580-3700 bit for bit; the chunked chain must equal the unchunked one."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import make_problem, null_model
+from test_parity_gpu import assert_results_close
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def jx():
+    from janusx_b200 import jxrs
+    yield jxrs
+    jxrs.clear_model_cache()
+
+
+def _read_all(reader, chunk, **kw):
+    gs, sites, afs, ms, sizes = [], [], [], [], []
+    while True:
+        out = reader.next_chunk_prepared(chunk, **kw)
+        if out is None:
+            break
+        g, s, af, miss = out
+        assert g.dtype == np.float32 and g.shape == (len(s), reader.n_samples) and af.shape == miss.shape == (len(s),)
+        gs.append(g); sites.extend(s); afs.append(af); ms.append(miss); sizes.append(len(s))
+    return np.concatenate(gs), sites, np.concatenate(afs), np.concatenate(ms), sizes
+
+
+def test_reader_rows_bit_exact_and_chunk_invariant(jx, oracle, tmp_path):
+    from janusx_b200 import synth
+    from janusx_b200.gfreader import BedChunkReader
+    n_full, m = 211, 700
+    packed, _ = synth.draw_genotypes(m, n_full, seed=17, missing_rate=0.04)
+    packed[5] = 0b01010101
+    packed[6] = 0
+    prefix = str(tmp_path / "rb")
+    ids = [f"rs{i}" if i % 9 else "." for i in range(m)]
+    synth.write_plink(prefix, packed, n_full, snp_ids=ids)
+    fam = oracle.read_fam(prefix)
+    sub_ids = [fam[i] for i in sorted(np.random.default_rng(2).choice(n_full, size=150, replace=False))]
+    sub_idx = np.array([fam.index(s) for s in sub_ids], dtype=np.int64)
+    for kw, sidx in ((dict(), None), (dict(sample_ids=sub_ids), sub_idx)):
+        for thr in ((0.02, 0.05, 1.0), (0.0, 1.0, 1.0), (0.05, 0.1, 0.45)):
+            keep, g_o, af_o, miss_o = oracle.bed_chunk_prepared_rows(packed, n_full, sidx, *thr)
+            rd = BedChunkReader(prefix, maf_threshold=thr[0], max_missing_rate=thr[1], het_threshold=thr[2], **kw)
+            assert rd.n_snps == m and rd.n_samples == (n_full if sidx is None else 150)
+            g, sites, af, miss, sizes = _read_all(rd, 128)
+            assert sizes[:-1] == [128] * (len(sizes) - 1) and sum(sizes) == int(keep.sum())   # chunks are filled up
+            assert np.array_equal(g.view(np.uint32), g_o.view(np.uint32))
+            assert np.array_equal(af.view(np.uint32), af_o.view(np.uint32)) and np.array_equal(miss, miss_o)
+            bim = oracle.read_bim(prefix)
+            assert [(s.chrom, s.snp, s.pos, s.ref_allele, s.alt_allele) for s in sites] == [bim[i] for i in np.nonzero(keep)[0]]
+            g2 = _read_all(BedChunkReader(prefix, maf_threshold=thr[0], max_missing_rate=thr[1], het_threshold=thr[2], **kw), 10_000)[0]
+            assert np.array_equal(g2.view(np.uint32), g.view(np.uint32))
+    # snp_range / snp_indices / snps_only and error messages
+    rd = BedChunkReader(prefix, snp_range=(100, 300))
+    assert rd.n_snps == 200 and sum(_read_all(rd, 64)[4]) == 200
+    rd = BedChunkReader(prefix, snp_indices=[7, 3, 500])
+    assert [s.pos for s in _read_all(rd, 2)[1]] == [oracle.read_bim(prefix)[i][2] for i in (7, 3, 500)]
+    with pytest.raises(RuntimeError, match="sample id not found"):
+        BedChunkReader(prefix, sample_ids=["nobody"])
+    with pytest.raises(RuntimeError, match="invalid snp_range"):
+        BedChunkReader(prefix, snp_range=(5, 5))
+    with pytest.raises(ValueError, match="chunk_size must be > 0"):
+        BedChunkReader(prefix).next_chunk_prepared(0)
+    assert jx.BedChunkReader is BedChunkReader
+
+
+def test_route_b_chain_matches_oracle(jx, oracle, tmp_path):
+    """reader -> LMM / LMM2 / FvLMM .gwas -> GwasAssocTsvWriter, chunked, against the oracle on the same rows."""
+    from janusx_b200 import assoc, synth
+    from janusx_b200.gfreader import BedChunkReader
+    case = make_problem(n=260, m=420, q=2, seed=23, missing_rate=0.03)
+    prefix = str(tmp_path / "chain")
+    synth.write_plink(prefix, case.packed, case.n)
+    K = case.u @ np.diag(case.s) @ case.u.T - 1e-6 * np.eye(case.n)       # LMM adds its own 1e-6 ridge
+    lmm = assoc.LMM(case.y, case.cov, K)
+    keep, g_o, af_o, miss_o = oracle.bed_chunk_prepared_rows(case.packed, case.n, None, 0.02, 0.05, 1.0)
+    ut = lmm.Dh
+    want = oracle.lmm_reml_chunk_from_snp_f32(lmm.S, lmm.Xcov, lmm.y[:, 0], lmm.bounds[0], lmm.bounds[1], g_o, ut, 30, 1e-2)
+    rd = BedChunkReader(prefix, maf_threshold=0.02, max_missing_rate=0.05)
+    w = jx.GwasAssocTsvWriter(str(tmp_path / "b.tsv"))
+    outs = []
+    while True:
+        nxt = rd.next_chunk_prepared(100)
+        if nxt is None:
+            break
+        g, sites, af, miss = nxt
+        res = lmm.gwas(g)
+        outs.append(res)
+        w.write_chunk(sites, [s.snp for s in sites], af, miss / np.float32(case.n), res)
+    w.close()
+    got = np.concatenate(outs)
+    assert_results_close(got, want)
+    assert w.rows_written == int(keep.sum())
+    lines = (tmp_path / "b.tsv").read_bytes().split(b"\n")
+    assert len(lines) == w.rows_written + 2 and lines[0].startswith(b"chrom\tpos\tsnp\tallele0\tallele1\taf\tmiss\tbeta")
+    bim = oracle.read_bim(prefix)
+    k0 = int(np.nonzero(keep)[0][0])
+    assert lines[1] + b"\n" == oracle.format_row(bim[k0][0], bim[k0][2], bim[k0][1], bim[k0][3], bim[k0][4], float(af_o[0]),
+                                                 float(np.float32(miss_o[0]) / np.float32(case.n)), got[0])
+    # LMM2 and FvLMM objects on the same chunks
+    lmm2 = assoc.LMM2(case.y, case.cov, K)
+    res2 = lmm2.gwas(g_o[:64])
+    want2 = oracle.lmm_reml_lmm2_chunk_from_snp_f32(lmm2.S, lmm2.Xcov, lmm2.y[:, 0], lmm2.bounds[0], lmm2.bounds[1], g_o[:64],
+                                                    lmm2.Dh, float(lmm2._lmm2_ml0_exact), 30, 1e-2)
+    assert_results_close(res2, want2, cols_p=(2, 5), cols_lambda=(3,))
+    fv = assoc.FvLMM(case.y, case.cov, K)
+    res3 = fv.gwas(g_o[:64])
+    want3 = oracle.lmm_assoc_chunk_from_snp_f32(fv.S, fv.Xcov, fv.y[:, 0], float(np.log10(fv.lbd_null)), g_o[:64], fv.Dh)
+    want3 = want3[0] if isinstance(want3, tuple) else want3
+    assert_results_close(res3, want3)
