@@ -179,3 +179,46 @@ def test_cli_argument_rules_and_vcf_cache(tmp_path, monkeypatch):
     gwas._vcf_cache(str(vcf), str(tmp_path), False)
     assert len(calls) == 2                                                                     # stale: rebuilt
     assert jxrs.default_device_batch(20000) == 151552 and jxrs.default_device_batch(50000) == 75776
+
+
+def test_packed_entry_point_validation_and_writer_text_paths(tmp_path):
+    """Argument checks of lmm_reml_assoc_packed_f32 (src/stats/lmm.rs:3089-3187: same messages, raised before any device
+    work) and the raw-text paths of GwasAssocTsvWriter (append_text / send_block / flush, assoc2tsv.rs:862-885)."""
+    from janusx_b200 import jxrs
+    n, m = 10, 4
+    bps = (n + 3) // 4
+    packed = np.zeros((m, bps), np.uint8)
+    s, xc, y, ut = np.ones(n), np.ones((n, 1)), np.zeros(n), np.eye(n, dtype=np.float32)
+    flip, maf = np.zeros(m, bool), np.zeros(m, np.float32)
+    call = lambda **kw: jxrs.lmm_reml_assoc_packed_f32(**{**dict(packed=packed, n_samples=n, row_flip=flip, row_maf=maf, s=s,
+                                                                 xcov=xc, y_rot=y, u_t=ut), **kw})
+    for kw, msg in ((dict(n_samples=0), "n_samples must be > 0"), (dict(low=1.0, high=1.0), "low must be < high"),
+                    (dict(tol=0.0), "tol must be positive and finite"), (dict(packed=np.zeros(5, np.uint8)), "packed must be 2D"),
+                    (dict(packed=np.zeros((m, bps + 1), np.uint8)), "packed second dimension mismatch: got 4, expected 3"),
+                    (dict(row_maf=maf[:-1]), "row_flip/row_maf length mismatch"),
+                    (dict(row_indices=[0, 9]), "row_indices out of range"),
+                    (dict(sample_indices=[0, 1]), "sample_indices length mismatch: got 2, expected 10"),
+                    (dict(n_samples=12, packed=np.zeros((m, 3), np.uint8)), "must equal n_samples=12 when sample_indices is not provided"),
+                    (dict(u_t=np.eye(n - 1, dtype=np.float32)), "u_t must be"), (dict(model="mult"), "model must be one of")):
+        with pytest.raises((RuntimeError, ValueError), match=msg):
+            call(**kw)
+    with pytest.raises(NotImplementedError):
+        call(row_flip=np.ones(m, bool))
+    w = jxrs.GwasAssocTsvWriter(str(tmp_path / "t.tsv"))
+    w.append_text("", True, 0)                                  # no-op: nothing opened yet
+    with pytest.raises(IOError):
+        w.send_block(b"x")                                      # writer not initialised
+    w.append_text("1\t5\trs1\tA\tG\t0.1000\t0.0000\t1.0000\t0.5000\t4.0000e0\t4.5500e-2\t5.0000e-2\n", True, 1)
+    w.send_block(b"# trailer\n")
+    w.flush()
+    with pytest.raises(ValueError, match="inconsistent results columns"):
+        w.append_text("x\n", False, 1)
+    w.close()
+    w.close()
+    lines = (tmp_path / "t.tsv").read_text().splitlines()
+    assert lines[0].endswith("pwald\tplrt") and lines[1].startswith("1\t5\trs1") and lines[2] == "# trailer" and w.rows_written == 1
+    cols = jxrs._read_bim_columns.__wrapped__ if hasattr(jxrs._read_bim_columns, "__wrapped__") else jxrs._read_bim_columns
+    (tmp_path / "p.bim").write_text("1\trs1\t0\t100\tA\tG\n2\t.\t0\tx\tC\tT\n")
+    chrom, pos, snp, a0, a1 = cols(str(tmp_path / "p"), None)
+    assert (chrom, pos, snp, a0, a1) == (["1", "2"], [100, 0], ["rs1", "."], ["A", "C"], ["G", "T"])
+    assert cols(str(tmp_path / "p"), [1])[2] == ["."]
