@@ -402,10 +402,10 @@ def main():
         fp64_core_peak = 36.0      # TFLOP/s: 18.0 T DFMA/s measured with tools/fp64_probe.cu (profiles/r1_fp64_probe.txt)
         # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu capture of this
         # exact default workload (profiles/r1_ncu_final_metrics.csv); null for any other configuration
-        # (solve: profiles/r1_ncu_lane_metrics.csv at 151,460 kept SNPs; rotation: r1_ncu_final_metrics.csv at 75,734;
+        # (solve: profiles/r1_ncu_lane_final.csv at 151,460 kept SNPs; rotation: r1_ncu_final_metrics.csv at 75,734;
         # bytes scale with the kept SNPs of the step)
         default_cfg = (n == 20000 and B % 75776 == 0 and args.model == "lmm2" and args.rotate_variant == 3 and q == 3)
-        solve_traffic = (920033189888 + 94335488) * (kept / 151460.0) if default_cfg else None
+        solve_traffic = (920233095680 + 210615296) * (kept / 151460.0) if default_cfg else None
         rot_traffic = (76375571200 + 12103506432 + 171910203648 + 6066589696) * (kept / 75734.0) if default_cfg else None
         rot_roof = {"kernel": ("rotate_dmma_kernel (FP64 DMMA GEMM)" if args.rotate_variant == 0 else
                                ("i8_rotate_kernel (tcgen05 int8-sliced exact rotation, 2 passes)" if args.rotate_variant == 3 else
@@ -422,7 +422,7 @@ def main():
                       "traffic": solve_traffic, "launch_ms": st["solve"],
                       "algorithmic_flop_per_launch": solve_flop,
                       "algorithmic_bytes_per_launch": (mean_evals * 2.0 + 1.0) * kept * n * 4.0,
-                      "traffic_source": "profiles/r1_ncu_lane_metrics.csv (ncu, same command); algorithmic bytes = the f32 "
+                      "traffic_source": "profiles/r1_ncu_lane_final.csv (ncu, same command); algorithmic bytes = the f32 "
                                         "rotated block streamed twice per objective evaluation (sums pass + residual pass) "
                                         "plus once for the validity check",
                       "peak_source": "2 x 18.0 T DFMA/s measured on this pool's B200 (tools/fp64_probe.cu); the algorithmic "
