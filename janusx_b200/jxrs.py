@@ -440,8 +440,10 @@ def lmm_assoc_chunk_f32(s, xcov, y_rot, log10_lbd, g_rot_chunk, threads=0, nullm
     return _get_model(s, xcov, y_rot).fixed_chunk(g_rot_chunk, log10_lbd, nullml, rotated=True)
 
 
-def lmm_assoc_chunk_from_snp_f32(s, xcov, y_rot, log10_lbd, snp_chunk, u_t, threads=0, nullml=None):
-    """src/stats/lmm.rs:2225-2238."""
+def lmm_assoc_chunk_from_snp_f32(s, xcov, y_rot, log10_lbd, snp_chunk, u_t, threads=0, nullml=None,
+                                 rotate_block_rows=512):
+    """src/stats/lmm.rs:2225-2238 (fvlmm_assoc_chunk_from_snp_f32, src/stats/fvlmm.rs:2114-2116, has the same signature;
+    the reference's Python passes all nine arguments positionally, pyBLUP/assoc.py:1512-1522)."""
     return _get_model(s, xcov, y_rot, u_t).fixed_chunk(snp_chunk, log10_lbd, nullml, rotated=False)
 
 
@@ -874,8 +876,9 @@ class FvLmmAssocCache:
     """src/stats/fvlmm.rs:1412-1436: handle of the fixed-lambda precomputation (weights, Cholesky of X'WX, ypy).
     Here the cached state lives with the device model; the object pins (model, log10 lambda)."""
 
-    def __init__(self, mdl: DeviceModel, log10_lbd: float):
+    def __init__(self, mdl: DeviceModel, log10_lbd: float, arrays=None):
         self._mdl, self._l10 = mdl, float(log10_lbd)
+        self._arrays = arrays                     # (s, xcov, y_rot) for the from-SNP variant, which also needs U^T
         self.n, self.p, self.lbd = mdl.n, mdl.p, 10.0 ** float(log10_lbd)
 
 
@@ -893,7 +896,7 @@ def fvlmm_assoc_prepare_cache_f32(s, xcov, y_rot, log10_lbd) -> FvLmmAssocCache:
     if not (math.isfinite(lbd) and lbd > 0.0):
         raise RuntimeError("invalid log10_lbd")
     # a private device model: the handle must outlive evictions from the array-argument cache
-    return FvLmmAssocCache(DeviceModel(s, xc, y), log10_lbd)
+    return FvLmmAssocCache(DeviceModel(s, xc, y), log10_lbd, (_f64(s).reshape(-1), xc, y))
 
 
 def fvlmm_assoc_chunk_with_cache_f32(cache: FvLmmAssocCache, g_rot_chunk, threads=0, nullml=None):
@@ -902,6 +905,51 @@ def fvlmm_assoc_chunk_with_cache_f32(cache: FvLmmAssocCache, g_rot_chunk, thread
     if g.ndim != 2 or g.shape[1] != cache.n:
         raise RuntimeError("g_rot_chunk must be (m, n)")
     return cache._mdl.fixed_chunk(g, cache._l10, nullml, rotated=True)
+
+
+def fvlmm_assoc_chunk_from_snp_with_cache_f32(cache: FvLmmAssocCache, snp_chunk, u_t, threads=0, nullml=None,
+                                              rotate_block_rows=512):
+    """src/stats/fvlmm.rs:1997-2060: the cached fixed-lambda scan of an unrotated chunk."""
+    g = np.asarray(snp_chunk)
+    if g.ndim != 2 or g.shape[1] != cache.n:
+        raise RuntimeError("snp_chunk must be (m, n)")
+    s_, xc_, y_ = cache._arrays
+    return _get_model(s_, xc_, y_, u_t).fixed_chunk(g, cache._l10, nullml, rotated=False)
+
+
+def fvlmm_assoc_chunk_from_snp_to_tsv_f32(s, xcov, y_rot, log10_lbd, snp_chunk, u_t, chrom, pos, snp, allele0, allele1, maf,
+                                          miss, threads=0, nullml=None, rotate_block_rows=512, progress_callback=None,
+                                          progress_every=0):
+    """src/stats/fvlmm.rs:2257-2480 -> ([tsv text blocks], rows): fixed-lambda scan of an unrotated chunk returned as
+    ready-made TSV rows (miss is a rate)."""
+    g = np.asarray(snp_chunk)
+    m = g.shape[0]
+    if any(len(c) != m for c in (chrom, pos, snp, allele0, allele1, maf, miss)):
+        raise RuntimeError(f"TSV metadata length mismatch: rows={m}")
+    res = lmm_assoc_chunk_from_snp_f32(s, xcov, y_rot, log10_lbd, g, u_t, threads, nullml)
+    if progress_callback is not None:
+        progress_callback(m, m)
+    if m == 0:
+        return [], 0
+    return [_format_block(chrom, pos, snp, allele0, allele1, maf, miss, res, "add")], m
+
+
+def _outside_scope(name):
+    def _f(*_a, **_k):
+        raise NotImplementedError(f"{name} belongs to a different algorithm (FaST-LMM low-rank / plain LM) and is outside "
+                                  "the exact-LMM path this library implements")
+    _f.__name__ = name
+    _f.__doc__ = "Present so that `from janusx.janusx import ...` in python/janusx/pyBLUP/assoc.py:207-218 resolves."
+    return _f
+
+
+# hard imports of the reference's Python layer that are not part of this path (pyBLUP/assoc.py:207-218)
+fastlmm_prepare_lowrank_f64 = _outside_scope("fastlmm_prepare_lowrank_f64")
+fastlmm_assoc_from_snp_f32 = _outside_scope("fastlmm_assoc_from_snp_f32")
+fastlmm_reml_chunk_f32 = _outside_scope("fastlmm_reml_chunk_f32")
+fastlmm_reml_null_f32 = _outside_scope("fastlmm_reml_null_f32")
+fastlmm_assoc_chunk_f32 = _outside_scope("fastlmm_assoc_chunk_f32")
+lm_block_assoc_f32 = _outside_scope("lm_block_assoc_f32")
 
 
 # ------------------------------------------------------------------------------------------------------
