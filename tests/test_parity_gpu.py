@@ -300,6 +300,20 @@ def test_packed_array_entry_points_and_tsv_writer(jx, oracle, tmp_path):
     assert_results_close(got_f, want_f, cols_p=(2, 3))
     with pytest.raises(RuntimeError, match="g_rot_chunk must be"):
         jx.fvlmm_assoc_chunk_with_cache_f32(cache, rot[:, :-1])
+    # unrotated chunk through the cache handle, and the variant that returns ready-made TSV text (positional calls as in
+    # pyBLUP/assoc.py:1512-1522 / workflow_model_stream.py:1680-1700)
+    got_s = jx.fvlmm_assoc_chunk_from_snp_with_cache_f32(cache, g, nm["ut"], 0, nm["ml0"], 512)
+    assert_results_close(got_s, want_f, cols_p=(2, 3))
+    got_9 = jx.fvlmm_assoc_chunk_from_snp_f32(case.s, nm["xcov"], nm["y"], l10, g, nm["ut"], 0, None, 512)
+    assert_results_close(got_9, want_f[:, :3])
+    names = [bim[int(i)] for i in idx]
+    blocks, n_rows = jx.fvlmm_assoc_chunk_from_snp_to_tsv_f32(
+        case.s, nm["xcov"], nm["y"], l10, g, nm["ut"], [b[0] for b in names], [b[2] for b in names], [b[1] for b in names],
+        [b[3] for b in names], [b[4] for b in names], af[idx].tolist(), rate_all.tolist(), threads=0, nullml=None)
+    assert n_rows == idx.size and len(blocks) == 1
+    first = blocks[0].split(b"\n")[0] + b"\n"
+    assert first == oracle.format_row(names[0][0], names[0][2], names[0][1], names[0][3], names[0][4], float(af[idx[0]]),
+                                      float(rate_all[0]), got_9[0])
 
 
 def test_sample_subset_scan(jx, oracle):
