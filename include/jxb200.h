@@ -128,6 +128,12 @@ int jxb_scan_packed_dev(jxb_model* m, const uint8_t* packed_dev, size_t bytes_pe
 int jxb_scan_fetch(jxb_model* m, size_t rows, int out_cols, uint8_t* keep_host, float* af_host,
                    int32_t* missing_host, double* out_host, int32_t* evals_host, size_t* n_kept_host);
 
+/* Device-to-device variant for callers that keep results in HBM (multi-GPU gather over NCCL): out_dst_dev
+ * f64[n_kept, out_cols] compacted, af_dst_dev f32[rows] and counts_dst_dev i32[rows, 4] = missing, het, hom_alt, keep
+ * by source row (any may be NULL).  Synchronises the model's stream; *n_kept_host = rows kept. */
+int jxb_scan_fetch_dev(jxb_model* m, size_t rows, int out_cols, double* out_dst_dev, float* af_dst_dev,
+                       int32_t* counts_dst_dev, size_t* n_kept_host);
+
 /* K1 alone, for parity tests: counts + QC + decode/centre of one packed batch.
  *   g_host nullable f32[n_kept, n] (compacted), counts_host i32[rows,4] = missing, het, hom_alt, keep */
 int jxb_decode_packed(jxb_model* m, const uint8_t* packed_host, size_t bytes_per_snp, size_t rows, size_t n_full,
@@ -147,6 +153,10 @@ int jxb_decode_packed_prepared(jxb_model* m, const uint8_t* packed_host, size_t 
  * JX_LMM_UNIFIED_STAGE_TIMING, src/stats/lmm.rs:2711-2742.)  Enabled by jxb_set_timing(1). */
 void jxb_set_timing(int on);
 int jxb_last_stage_ms(jxb_model* m, float ms6[6]);
+/* Measured FP64 CUDA-core issue rate of `device`, in 1e12 lane-instructions per second: tops3 = {DFMA, DADD, DMUL}
+ * (register-resident chains; tools/fp64_probe.cu is the stand-alone version).  The solve kernels are compiled without
+ * FMA contraction (reference rounding), so their ceiling is the DADD/DMUL rate; bench.py reports against it. */
+int jxb_fp64_probe(int device, double tops3[3]);
 /* raw stream handle (cudaStream_t) the model launches on, for callers timing with CUDA events */
 void* jxb_model_stream(jxb_model* m);
 /* rotation kernel for subsequent packed additive scans: 3 = hand-written tcgen05 int8-sliced exact rotation
@@ -159,6 +169,14 @@ void jxb_set_thread_solve_min_rows(size_t rows);
 /* Kernel for those large batches: 0 (default) = lane-per-SNP with refill on the row-major block, 1 = the earlier
  * thread-per-SNP kernel on an SNP-minor block (tcgen05 rotation only).  Same per-SNP arithmetic, identical results. */
 void jxb_set_big_solve_kernel(int variant);
+/* Streamed scan (default on): large additive LMM / LMM2 batches are rotated in slabs of `slab_rows` rows (0 = keep the
+ * current value, default 8192) while ONE persistent solve kernel consumes the rows already rotated -- the tensor pipe
+ * (rotation) and the FP64 pipe (solve) of every SM work at the same time.  Same kernels' arithmetic, identical results.
+ * on = 0 restores rotate-then-solve. */
+void jxb_set_stream_overlap(int on, size_t slab_rows);
+/* jxb_last_stage_ms plus [6] = duration of the solve kernel on its own stream, [7] = 1 when the last scan was
+ * streamed (then [2] is the rotation of all slabs and [3] the part of the solve left after the last slab). */
+int jxb_last_stage_ms8(jxb_model* m, float ms8[8]);
 
 /* ---- file level ------------------------------------------------------------------------------------
  * lmm_reml_assoc_bed_to_tsv_f32 / lmm_reml_lmm2_assoc_bed_to_tsv_f32 / fvlmm_assoc_bed_to_tsv_f32 --
@@ -190,7 +208,9 @@ int jxb_scan_bed_to_tsv(jxb_model* m, const jxb_bed_scan_cfg* cfg, size_t* rows_
                         void* user);
 
 /* TSV row formatter (append_assoc_row_from_fields, src/io/assoc2tsv.rs:430-517); exported for tests.
- * Returns bytes written. */
+ * Returns bytes written.  Never writes past buf[cap-1]: when cap is below the worst case for these strings
+ * (2*strlen(chrom) + strlen(snp) + strlen(a0) + strlen(a1) + 3088) nothing useful is written and the return value is
+ * that size (> cap) -- call again with a buffer at least that large.  (Rust's String has no row length limit.) */
 size_t jxb_format_row(char* buf, size_t cap, const char* chrom, int64_t pos, const char* snp, const char* a0,
                       const char* a1, float af, float miss_rate, const double* row, int out_cols);
 

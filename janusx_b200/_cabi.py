@@ -75,6 +75,7 @@ SYMBOLS = {
     "jxb_scan_packed_dev": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_size_t, _vp, C.POINTER(QcCfg),
                                       C.POINTER(SolveCfg), C.c_int]),
     "jxb_scan_fetch": (C.c_int, [_vp, C.c_size_t, C.c_int, _vp, _vp, _vp, _vp, _vp, _psz]),
+    "jxb_scan_fetch_dev": (C.c_int, [_vp, C.c_size_t, C.c_int, _vp, _vp, _vp, _psz]),
     "jxb_decode_packed": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_size_t, _vp, C.POINTER(QcCfg), _vp, _vp,
                                     _vp, _vp, _psz]),
     "jxb_decode_packed_prepared": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_size_t, _vp, _vp, _vp, C.c_int, _vp,
@@ -82,9 +83,12 @@ SYMBOLS = {
     "jxb_set_timing": (None, [C.c_int]),
     "jxb_last_stage_ms": (C.c_int, [_vp, _pf]),
     "jxb_model_stream": (_vp, [_vp]),
+    "jxb_fp64_probe": (C.c_int, [C.c_int, _pd]),
     "jxb_set_rotate_variant": (None, [C.c_int]),
     "jxb_set_thread_solve_min_rows": (None, [C.c_size_t]),
     "jxb_set_big_solve_kernel": (None, [C.c_int]),
+    "jxb_set_stream_overlap": (None, [C.c_int, C.c_size_t]),
+    "jxb_last_stage_ms8": (C.c_int, [_vp, _pf]),
     "jxb_scan_bed_to_tsv": (C.c_int, [_vp, C.POINTER(BedScanCfg), _psz, PROGRESS_CB, _vp]),
     "jxb_format_row": (C.c_size_t, [C.c_char_p, C.c_size_t, C.c_char_p, C.c_int64, C.c_char_p, C.c_char_p,
                                     C.c_char_p, C.c_float, C.c_float, _pd, C.c_int]),

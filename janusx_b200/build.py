@@ -14,7 +14,7 @@ OUT = PKG / "libjxb200.so"
 # heavy fully-unrolled K3 kernels build in parallel.
 UNITS = [("cabi.cu", "cabi", []), ("k1_decode.cu", "k1_decode", []), ("k2_rotate.cu", "k2_rotate", []), ("k2_int8.cu", "k2_int8", []), ("k2_i8mma.cu", "k2_i8mma", []),
          ("k3_solve.cu", "k3_solve", ["-fmad=false"]), ("bed_scan.cpp", "bed_scan", []), ("grm.cu", "grm", []), ("eigh.cu", "eigh", []),
-         ("vcf_cache.cpp", "vcf_cache", [])]
+         ("vcf_cache.cpp", "vcf_cache", []), ("probe.cu", "probe", [])]
 # -fmad=false: K3 reproduces the reference's separate multiply/add rounding (Rust never fuses)
 _K3X = os.environ.get("JXB_K3_FLAGS", "").split()   # e.g. "-DJXB_K3_BUFS=1 -DJXB_K3_MINB=4" (tuning experiments)
 UNITS += [("k3_inst.cu", f"k3_inst_p{p}", [f"-DJXB_P={p}", "-fmad=false", *_K3X]) for p in range(1, 9)]

@@ -182,16 +182,21 @@ struct Writer {
                 const size_t lo = k * t / nth, hi = k * (t + 1) / nth;
                 std::string& text = parts[t];
                 text.reserve((hi - lo) * 112);
-                char buf[2048];
+                std::vector<char> buf(4096);   // grown on demand: BIM alleles (indels, SVs) have no length limit
                 for (size_t i = lo; i < hi; ++i) {
                     const size_t r = kept_rows[i];
                     const Site& s = b->sites[r];
                     // lmm.rs:2667-2670: miss column = missing_count as f32 / n as f32
                     const float mr = n_model ? (float)b->missing[r] / (float)n_model : 0.0f;
-                    const size_t len = jxb_format_row(buf, sizeof buf, s.chrom.c_str(), s.pos, s.snp.c_str(),
-                                                      s.a0.c_str(), s.a1.c_str(), b->af[r], mr,
-                                                      b->out.data() + i * b->out_cols, b->out_cols);
-                    text.append(buf, len);
+                    size_t len = jxb_format_row(buf.data(), buf.size(), s.chrom.c_str(), s.pos, s.snp.c_str(),
+                                                s.a0.c_str(), s.a1.c_str(), b->af[r], mr,
+                                                b->out.data() + i * b->out_cols, b->out_cols);
+                    if (len > buf.size()) {
+                        buf.resize(len);
+                        len = jxb_format_row(buf.data(), buf.size(), s.chrom.c_str(), s.pos, s.snp.c_str(), s.a0.c_str(),
+                                             s.a1.c_str(), b->af[r], mr, b->out.data() + i * b->out_cols, b->out_cols);
+                    }
+                    text.append(buf.data(), len);
                 }
             };
             if (nth == 1) {
@@ -236,9 +241,19 @@ const char* header_for(int out_cols) {
 
 }  // namespace
 
+// Bytes a row can need: the strings verbatim (chrom twice for the chrom_pos fallback name) plus nine numeric fields
+// (a `{:.4}` rendering of a huge finite double is ~315 characters) plus separators.
+static size_t format_row_need(const char* chrom, const char* snp, const char* a0, const char* a1) {
+    return 2 * strlen(chrom) + strlen(snp) + strlen(a0) + strlen(a1) + 9 * 336 + 64;
+}
+
+// Never writes past buf[cap-1].  Returns the row length when it fitted; otherwise a value > cap (the size that is
+// guaranteed to fit) and the buffer content is unspecified -- callers retry with a larger buffer.
 static size_t format_row_impl(char* buf, size_t cap, const char* chrom, int64_t pos, const char* snp,
                               const char* a0, const char* a1, float af, float miss_rate, const double* row,
                               int out_cols, bool resolve_name) {
+    const size_t need = format_row_need(chrom, snp, a0, a1);
+    if (cap < need) return need > cap ? need : cap + 1;
     const double beta = row[0], se = row[1];
     const bool valid = std::isfinite(beta) && std::isfinite(se) && se > 0.0;
     // sanitize_assoc_pvalue, src/math/linalg.rs:99-108
@@ -252,30 +267,33 @@ static size_t format_row_impl(char* buf, size_t cap, const char* chrom, int64_t 
     if (valid) { const double z = beta / se; chisq = z * z; }
     char* w = buf;
     char* end = buf + cap;
-    auto put_s = [&](const char* s) { w += snprintf(w, (size_t)(end - w), "%s", s); };
+    // snprintf reports the untruncated length: clamp so `w` can never leave the buffer
+    auto adv = [&](size_t k) { const size_t room = (size_t)(end - w) - 1; w += k < room ? k : room; };
+    auto put_s = [&](const char* s) { const size_t k = strlen(s), room = (size_t)(end - w) - 1; const size_t c = k < room ? k : room; memcpy(w, s, c); w += c; };
     auto tab = [&]() { if (w < end - 1) *w++ = '\t'; };
     put_s(chrom); tab();
-    w += snprintf(w, (size_t)(end - w), "%lld", (long long)pos); tab();
+    adv((size_t)snprintf(w, (size_t)(end - w), "%lld", (long long)pos)); tab();
     if (resolve_name && (snp[0] == '\0' || (snp[0] == '.' && snp[1] == '\0'))) {
-        w += snprintf(w, (size_t)(end - w), "%s_%lld", chrom, (long long)pos);
+        put_s(chrom);
+        adv((size_t)snprintf(w, (size_t)(end - w), "_%lld", (long long)pos));
     } else {
         put_s(snp);
     }
     tab();
     put_s(a0); tab();
     put_s(a1); tab();
-    w += fmt_fixed(w, (size_t)(end - w), (double)af, 4); tab();
-    w += fmt_fixed(w, (size_t)(end - w), (double)miss_rate, 4); tab();
-    w += fmt_fixed(w, (size_t)(end - w), beta, 4); tab();
-    w += fmt_fixed(w, (size_t)(end - w), se, 4); tab();
-    w += fmt_exp(w, (size_t)(end - w), chisq, 4); tab();
-    w += fmt_exp(w, (size_t)(end - w), pw, 4);
+    adv(fmt_fixed(w, (size_t)(end - w), (double)af, 4)); tab();
+    adv(fmt_fixed(w, (size_t)(end - w), (double)miss_rate, 4)); tab();
+    adv(fmt_fixed(w, (size_t)(end - w), beta, 4)); tab();
+    adv(fmt_fixed(w, (size_t)(end - w), se, 4)); tab();
+    adv(fmt_exp(w, (size_t)(end - w), chisq, 4)); tab();
+    adv(fmt_exp(w, (size_t)(end - w), pw, 4));
     if (out_cols == 4) {
-        tab(); w += fmt_exp(w, (size_t)(end - w), row[3], 4);
+        tab(); adv(fmt_exp(w, (size_t)(end - w), row[3], 4));
     } else if (out_cols == 6) {
-        tab(); w += fmt_exp(w, (size_t)(end - w), row[3], 6);
-        tab(); w += fmt_exp(w, (size_t)(end - w), row[4], 6);
-        tab(); w += fmt_exp(w, (size_t)(end - w), row[5], 4);
+        tab(); adv(fmt_exp(w, (size_t)(end - w), row[3], 6));
+        tab(); adv(fmt_exp(w, (size_t)(end - w), row[4], 6));
+        tab(); adv(fmt_exp(w, (size_t)(end - w), row[5], 4));
     }
     if (w < end - 1) *w++ = '\n';
     *w = '\0';
@@ -308,7 +326,7 @@ extern "C" size_t jxb_format_block(char* buf, size_t cap, size_t rows, const cha
     std::vector<char> line;
     for (size_t r = 0; r < rows; ++r) {
         alleles_by_model(a0, a1, genetic_model, t0, t1);
-        const size_t need = strlen(chrom) * 2 + strlen(snp) + t0.size() + t1.size() + 512;
+        const size_t need = format_row_need(chrom, snp, t0.c_str(), t1.c_str());
         if (line.size() < need) line.resize(need);
         // write_chunk prints the caller's SNP names verbatim (no chrom_pos substitution)
         const size_t len = format_row_impl(line.data(), line.size(), chrom, pos[r], snp, t0.c_str(), t1.c_str(), af[r],

@@ -12,11 +12,18 @@
 struct jxb_model {
     jxb::Model m;
     bool timing_ready = false;
-    cudaEvent_t ev[8];
-    bool ev_rec[8] = {false, false, false, false, false, false, false, false};
-    float stage_ms[6] = {0, 0, 0, 0, 0, 0};
+    cudaEvent_t ev[10];
+    bool ev_rec[10] = {false, false, false, false, false, false, false, false, false, false};
+    float stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     float* missr = nullptr;       // [cap_rows] device
     uint8_t* mask = nullptr;      // [cap_rows] device (pre-keep mask)
+    float* prep_af = nullptr;     // [cap_rows] device: caller-supplied allele frequency per source row (prepared metadata)
+    uint8_t* prep_flip = nullptr; // [cap_rows] device: caller-supplied row_flip
+    // streamed scan: the solve runs on stream2 while m.stream still rotates later row slabs
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_slab0 = nullptr, ev_solve = nullptr;
+    bool last_streamed = false;
+    size_t last_nk = 0;           // kept rows of the last scan (known on the host after the decode stage)
     double* scal = nullptr;       // small device scratch (null fit outputs)
     size_t last_rows = 0;
     bool rot_dirty = false;       // rot holds a transposed block: re-zero before the row-major kernels read padding
@@ -34,6 +41,8 @@ static int g_timing = 0;
 static int g_rotate_variant = 3;
 static size_t g_thread_solve_min_rows = 32768;   // batches at least this large use the large-batch solve kernels
 static int g_big_solve_kernel = 0;               // 0 = lane-per-SNP with refill (row-major block), 1 = thread-per-SNP (SNP-minor)
+static int g_stream_overlap = 1;                 // 1 = large additive LMM/LMM2 batches rotate and solve concurrently (scan_streamed)
+static size_t g_stream_slab_rows = 8192;         // rows per rotation slab of the streamed scan (multiple of 256)
 
 void set_error(const std::string& msg) { g_err = msg; }
 int fail(int code, const std::string& msg) {
@@ -57,6 +66,16 @@ __global__ void widen_ut_kernel(const float* __restrict__ src, size_t n, size_t 
 __global__ void apply_mask_kernel(int32_t* counts, const uint8_t* mask, int rows) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r < rows && mask[r] == 0) counts[4 * r + 3] = 0;
+}
+
+// Prepared row metadata (src/stats/lmm.rs:1237-1262; decode.rs:213-219): the caller's allele frequency replaces the
+// one counted on the device (it is the imputation mean the reference uses, whatever samples it was computed over) and
+// row_flip travels in bit 1 of the keep word to the decode kernels.
+__global__ void apply_prepared_kernel(int32_t* counts, float* af, const float* row_af, const uint8_t* row_flip, int rows) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    if (row_af) af[r] = row_af[r];
+    if (row_flip && row_flip[r] && counts[4 * r + 3] != 0) counts[4 * r + 3] |= 2;
 }
 
 template <class T>
@@ -173,6 +192,8 @@ int ensure_capacity(jxb_model* h, size_t rows, size_t bps, bool need_g) {
         rc |= dev_alloc(&m.af, cap);
         rc |= dev_alloc(&h->missr, cap);
         rc |= dev_alloc(&h->mask, cap);
+        rc |= dev_alloc(&h->prep_af, cap);
+        rc |= dev_alloc(&h->prep_flip, cap);
         rc |= dev_alloc(&m.src_row, cap);
         if (m.g64) { cudaFree(m.g64); m.g64 = nullptr; }
         if (m.packed) { cudaFree(m.packed); m.packed = nullptr; m.bps_cap = 0; }
@@ -218,7 +239,14 @@ int ensure_stage_f32(Model& m, size_t count) {
     return 0;
 }
 
-int ensure_sample_idx(Model& m, const int64_t* idx, size_t n_sel, bool on_device) {
+int ensure_sample_idx(Model& m, const int64_t* idx, size_t n_sel, bool on_device, size_t n_full) {
+    if (!on_device) {
+        // the kernels index packed rows with these values unchecked: one host pass over n entries
+        for (size_t k = 0; k < n_sel; ++k)
+            if (idx[k] < 0 || (size_t)idx[k] >= n_full)
+                return fail(-2, "sample_idx[" + std::to_string(k) + "]=" + std::to_string((long long)idx[k]) +
+                                    " is outside [0, n_full=" + std::to_string(n_full) + ")");
+    }
     if (n_sel > m.n_sel_cap) {
         JXB_CUDA_OK(cudaStreamSynchronize(m.stream));
         if (m.sample_idx) cudaFree(m.sample_idx);
@@ -231,14 +259,88 @@ int ensure_sample_idx(Model& m, const int64_t* idx, size_t n_sel, bool on_device
     return 0;
 }
 
-void tick(jxb_model* h, int i) {
+void tick(jxb_model* h, int i, cudaStream_t st = nullptr) {
     if (!g_timing) return;
     if (!h->timing_ready) {
         for (auto& e : h->ev) cudaEventCreate(&e);
         h->timing_ready = true;
     }
-    cudaEventRecord(h->ev[i], h->m.stream);
+    cudaEventRecord(h->ev[i], st ? st : h->m.stream);
     h->ev_rec[i] = true;
+}
+
+SolveParams to_params(const jxb_solve_cfg* c, int mode);
+int out_cols_of(const jxb_solve_cfg* c, int mode);
+
+// ---- streamed scan -------------------------------------------------------------------------------------------------
+// Rotation (tensor pipe) and per-SNP solve (FP64 pipe) of ONE batch at the same time on the same SMs: the decoded
+// batch is rotated in slabs of g_stream_slab_rows rows on m.stream; after the first slab a single persistent
+// solve_lane_stream_kernel starts on stream2 and consumes rows as the rotation publishes them (sync[1]).  Three solve
+// CTAs (128 threads x 136 registers, 25 KB) and one SLIM i8_rotate_kernel CTA (192 x 64 registers, 121 KB) fit one SM
+// together; streamed_feasible() checks that from the compiled kernels' own attributes before the mode is used, and the
+// solve kernel carries a watchdog, so a rotation that cannot become resident is an error, never a hang.
+bool streamed_feasible(Model& m) {
+    static int cache[5] = {0, 0, 0, 0, 0};   // per covariate count: 0 unknown, 1 yes, -1 no
+    if (m.p < 1 || m.p > 4) return false;
+    if (cache[m.p] == 0) {
+        int r_regs = 0, r_smem = 0, s_regs = 0, s_smem = 0;
+        bool ok = rotate_slim_resources(&r_regs, &r_smem) == 0 && solve_lane_stream_resources(m.p, &s_regs, &s_smem) == 0;
+        if (ok) {
+            cudaDeviceProp prop;
+            ok = cudaGetDeviceProperties(&prop, m.device) == cudaSuccess;
+            if (ok) {
+                // allocation granularity: 256 registers per warp, 1 KB of shared memory reserved per CTA
+                auto warp_regs = [](int r) { return (r * 32 + 255) / 256 * 256; };
+                const int regs = 3 * 4 * warp_regs(s_regs) + 6 * warp_regs(r_regs);
+                const size_t smem = 3 * (size_t)(s_smem + 1024) + (size_t)(r_smem + 1024);
+                // ... and a 4th solve CTA must not be able to take the rotation's slot
+                ok = regs <= prop.regsPerMultiprocessor && smem <= prop.sharedMemPerMultiprocessor &&
+                     4 * 4 * warp_regs(s_regs) > prop.regsPerMultiprocessor;
+            }
+        }
+        cache[m.p] = ok ? 1 : -1;
+    }
+    return cache[m.p] == 1;
+}
+
+int scan_streamed(jxb_model* h, size_t nk, bool has_missing, const jxb_solve_cfg* cfg, int mode) {
+    Model& m = h->m;
+    if (!h->stream2) {
+        JXB_CUDA_OK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+        JXB_CUDA_OK(cudaEventCreateWithFlags(&h->ev_slab0, cudaEventDisableTiming));
+        JXB_CUDA_OK(cudaEventCreateWithFlags(&h->ev_solve, cudaEventDisableTiming));
+    }
+    const size_t slab = std::max<size_t>(256, g_stream_slab_rows / 256 * 256);
+    int rc = prepare_rotate_tc(m, std::min(round_up(slab, 128), m.a8_rows));
+    if (rc) return rc;
+    rc = ensure_solve_lane_buffers(m, nk, m.stream);
+    if (rc) return rc;
+    const int oc = out_cols_of(cfg, mode);
+    h->last_out_cols = oc;
+    int32_t* sync = m.n_kept + 4;   // {queue, ready, abort}
+    JXB_CUDA_OK(cudaMemsetAsync(sync, 0, 3 * sizeof(int32_t), m.stream));
+    for (size_t r0 = 0; r0 < nk; r0 += slab) {
+        const size_t r1 = std::min(nk, r0 + slab);
+        rc = launch_rotate_int8_tc_slab(m, r0, r1, has_missing, true, m.stream);
+        if (rc) return rc;
+        rc = launch_row_ssq_publish(m, m.rot, m.ldc, r0, r1, sync, m.stream);
+        note_launch(2);
+        if (rc) return rc;
+        if (r0 == 0) {
+            JXB_CUDA_OK(cudaEventRecord(h->ev_slab0, m.stream));
+            JXB_CUDA_OK(cudaStreamWaitEvent(h->stream2, h->ev_slab0, 0));
+            tick(h, 8, h->stream2);
+            rc = launch_solve_lane_stream(m, m.rot, m.ldc, nk, to_params(cfg, mode), m.out, oc, m.evals, sync, h->stream2);
+            note_launch(1);
+            if (rc) return rc;
+            tick(h, 9, h->stream2);
+            JXB_CUDA_OK(cudaEventRecord(h->ev_solve, h->stream2));
+        }
+    }
+    tick(h, 4);                                                 // rotation done (solve still running)
+    JXB_CUDA_OK(cudaStreamWaitEvent(m.stream, h->ev_solve, 0)); // join: later work on m.stream sees the results
+    h->last_streamed = true;
+    return 0;
 }
 
 SolveParams to_params(const jxb_solve_cfg* c, int mode) {
@@ -333,6 +435,8 @@ int scan_device_stages(jxb_model* h, const uint8_t* packed_dev, size_t bps, size
                        const int64_t* sidx_dev, size_t n_sel, bool have_mask, const jxb_qc_cfg* qc,
                        const jxb_solve_cfg* cfg, int mode) {
     Model& m = h->m;
+    h->last_nk = (size_t)-1;    // unknown on the host until the decode stage of the int8 path reads it back
+    h->last_streamed = false;
     int rc = clean_rot(h);
     if (rc) return rc;
     tick(h, 1);
@@ -365,6 +469,17 @@ int scan_device_stages(jxb_model* h, const uint8_t* packed_dev, size_t bps, size
         JXB_CUDA_OK(cudaStreamSynchronize(m.stream));
         // large batches: SNP-minor output + one-thread-per-SNP solve (no shared-memory transposition)
         const bool big = mode != 2 && m.p <= 8 && (size_t)nk >= g_thread_solve_min_rows;
+        h->last_streamed = false;
+        h->last_nk = (size_t)nk;
+        if (big && g_big_solve_kernel == 0 && g_rotate_variant == 3 && g_stream_overlap && streamed_feasible(m)) {
+            rc = clean_rot(h);
+            if (rc) return rc;
+            rc = scan_streamed(h, (size_t)nk, anym != 0, cfg, mode);
+            if (rc) return rc;
+            tick(h, 5);
+            h->last_rows = rows;
+            return 0;
+        }
         const bool lane_solve = big && g_big_solve_kernel == 0;
         const bool thread_solve = big && !lane_solve && g_rotate_variant == 3;
         if (lane_solve) {
@@ -423,6 +538,30 @@ int scan_device_stages(jxb_model* h, const uint8_t* packed_dev, size_t bps, size
     return 0;
 }
 
+// stage timers of the last scan from the recorded events (call after the stream has been synchronised)
+void collect_stage_ms(jxb_model* h) {
+    if (g_timing && h->timing_ready) {
+    for (int i = 0; i < 8; ++i) h->stage_ms[i] = 0.f;
+    auto span = [&](int a, int b) -> float {
+        float t = 0.f;
+        if (h->ev_rec[a] && h->ev_rec[b] && cudaEventElapsedTime(&t, h->ev[a], h->ev[b]) == cudaSuccess) return t;
+        (void)cudaGetLastError();  // an unrecorded pair must not poison later launch checks
+        return 0.f;
+    };
+    h->stage_ms[0] = span(1, 2);
+    h->stage_ms[1] = span(2, 3);
+    h->stage_ms[2] = span(3, 4);
+    h->stage_ms[3] = span(4, 5);
+    h->stage_ms[4] = span(0, 1);
+    h->stage_ms[5] = span(5, 6);
+    // streamed scan: [2] = rotation of all slabs (the solve runs underneath from the second slab on), [3] = what is
+    // left of the solve after the last slab, [6] = the solve kernel's own duration on its stream, [7] = 1
+    h->stage_ms[6] = h->last_streamed ? span(8, 9) : h->stage_ms[3];
+    h->stage_ms[7] = h->last_streamed ? 1.f : 0.f;
+    for (bool& r : h->ev_rec) r = false;
+}
+}
+
 int check_scan_args(jxb_model* h, size_t bps, size_t n_full, const int64_t* sidx, const jxb_qc_cfg* qc) {
     if (!h) return fail(-2, "model is null");
     if (!qc) return fail(-2, "qc cfg is null");
@@ -457,6 +596,10 @@ void jxb_set_timing(int on) { g_timing = on; }
 void jxb_set_rotate_variant(int variant) { g_rotate_variant = variant; }
 void jxb_set_thread_solve_min_rows(size_t rows) { g_thread_solve_min_rows = rows; }
 void jxb_set_big_solve_kernel(int variant) { g_big_solve_kernel = variant == 1 ? 1 : 0; }
+void jxb_set_stream_overlap(int on, size_t slab_rows) {
+    g_stream_overlap = on ? 1 : 0;
+    if (slab_rows) g_stream_slab_rows = slab_rows;
+}
 
 int jxb_model_create(int device, size_t n, size_t p, const double* s, const double* xcov, const double* y,
                      const float* u_t, jxb_model** out) {
@@ -496,12 +639,16 @@ void jxb_model_destroy(jxb_model* h) {
     if (m.stream) cudaStreamSynchronize(m.stream);
     void* ptrs[] = {m.s, m.y, m.xt, m.rec, m.ut, m.g64, m.rot, m.log_table, m.ssq, m.out, m.evals, m.packed, m.counts, m.af, m.src_row,
                     m.n_kept, m.sample_idx, m.stage_f32, m.fx_w, m.fx_py, m.fx_wx, m.fx_scal, h->missr, h->mask,
+                    h->prep_af, h->prep_flip,
                     h->scal, m.q8, m.q8_inv_scale, m.q8_rk, m.a8, m.coef, m.flags8, m.c32, m.lt_ws, m.corr64};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->timing_ready)
         for (auto& e : h->ev) cudaEventDestroy(e);
     if (m.stream) cudaStreamDestroy(m.stream);
+    if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
+    if (h->ev_slab0) cudaEventDestroy(h->ev_slab0);
+    if (h->ev_solve) cudaEventDestroy(h->ev_solve);
     for (void* t : {m.tmap_a8, m.tmap_q8_7, m.tmap_q8_3})
         if (t) free(t);
     if (m.tmap_ut) free(m.tmap_ut);
@@ -656,11 +803,15 @@ int jxb_scan_fetch(jxb_model* h, size_t rows, int out_cols, uint8_t* keep_host, 
     if (rows == 0) { if (n_kept_host) *n_kept_host = 0; return 0; }
     if (rows > m.cap_rows) return fail(-2, "rows exceeds the last scan");
     std::vector<int32_t> counts(rows * 4);
-    int32_t nk = 0;
+    int32_t scal[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     JXB_CUDA_OK(cudaMemcpyAsync(counts.data(), m.counts, rows * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, m.stream));
-    JXB_CUDA_OK(cudaMemcpyAsync(&nk, m.n_kept, sizeof(int32_t), cudaMemcpyDeviceToHost, m.stream));
+    JXB_CUDA_OK(cudaMemcpyAsync(scal, m.n_kept, sizeof scal, cudaMemcpyDeviceToHost, m.stream));
     if (af_host) JXB_CUDA_OK(cudaMemcpyAsync(af_host, m.af, rows * sizeof(float), cudaMemcpyDeviceToHost, m.stream));
     JXB_CUDA_OK(cudaStreamSynchronize(m.stream));
+    const int32_t nk = scal[0];
+    if (h->last_streamed && scal[6] != 0)
+        return fail(-50, "streamed scan: the solve kernel gave up waiting for rotated rows (rotation kernel not co-resident); "
+                         "disable the overlap with jxb_set_stream_overlap(0)");
     if (out_host && nk > 0)
         JXB_CUDA_OK(cudaMemcpyAsync(out_host, m.out, (size_t)nk * out_cols * sizeof(double), cudaMemcpyDeviceToHost, m.stream));
     if (evals_host && nk > 0)
@@ -672,22 +823,37 @@ int jxb_scan_fetch(jxb_model* h, size_t rows, int out_cols, uint8_t* keep_host, 
         if (missing_host) missing_host[r] = counts[4 * r + 0];
     }
     if (n_kept_host) *n_kept_host = (size_t)nk;
-    if (g_timing && h->timing_ready) {
-        for (int i = 0; i < 6; ++i) h->stage_ms[i] = 0.f;
-        auto span = [&](int a, int b) -> float {
-            float t = 0.f;
-            if (h->ev_rec[a] && h->ev_rec[b] && cudaEventElapsedTime(&t, h->ev[a], h->ev[b]) == cudaSuccess) return t;
-            (void)cudaGetLastError();  // an unrecorded pair must not poison later launch checks
-            return 0.f;
-        };
-        h->stage_ms[0] = span(1, 2);
-        h->stage_ms[1] = span(2, 3);
-        h->stage_ms[2] = span(3, 4);
-        h->stage_ms[3] = span(4, 5);
-        h->stage_ms[4] = span(0, 1);
-        h->stage_ms[5] = span(5, 6);
-        for (bool& r : h->ev_rec) r = false;
+    collect_stage_ms(h);
+    return 0;
+}
+
+int jxb_scan_fetch_dev(jxb_model* h, size_t rows, int out_cols, double* out_dst_dev, float* af_dst_dev,
+                       int32_t* counts_dst_dev, size_t* n_kept_host) {
+    if (!h) return fail(-2, "model is null");
+    Model& m = h->m;
+    JXB_CUDA_OK(cudaSetDevice(m.device));
+    if (rows == 0) { if (n_kept_host) *n_kept_host = 0; return 0; }
+    if (rows > m.cap_rows) return fail(-2, "rows exceeds the last scan");
+    int32_t scal[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    JXB_CUDA_OK(cudaMemcpyAsync(scal, m.n_kept, sizeof scal, cudaMemcpyDeviceToHost, m.stream));
+    if (h->last_nk == (size_t)-1) {
+        JXB_CUDA_OK(cudaStreamSynchronize(m.stream));
+        h->last_nk = (size_t)scal[0];
     }
+    const size_t nk_known = h->last_nk;
+    if (out_dst_dev && nk_known > 0)
+        JXB_CUDA_OK(cudaMemcpyAsync(out_dst_dev, m.out, nk_known * out_cols * sizeof(double), cudaMemcpyDeviceToDevice, m.stream));
+    if (af_dst_dev) JXB_CUDA_OK(cudaMemcpyAsync(af_dst_dev, m.af, rows * sizeof(float), cudaMemcpyDeviceToDevice, m.stream));
+    if (counts_dst_dev)
+        JXB_CUDA_OK(cudaMemcpyAsync(counts_dst_dev, m.counts, rows * 4 * sizeof(int32_t), cudaMemcpyDeviceToDevice, m.stream));
+    tick(h, 6);
+    JXB_CUDA_OK(cudaStreamSynchronize(m.stream));
+    if (h->last_streamed && scal[6] != 0)
+        return fail(-50, "streamed scan: the solve kernel gave up waiting for rotated rows (rotation kernel not co-resident); "
+                         "disable the overlap with jxb_set_stream_overlap(0)");
+    if ((size_t)scal[0] != nk_known) return fail(-51, "internal error: kept-row count changed between scan and fetch");
+    if (n_kept_host) *n_kept_host = nk_known;
+    collect_stage_ms(h);
     return 0;
 }
 
@@ -708,7 +874,7 @@ int jxb_scan_packed(jxb_model* h, const uint8_t* packed, size_t bps, size_t rows
     JXB_CUDA_OK(cudaMemcpyAsync(m.packed, packed, rows * bps, cudaMemcpyHostToDevice, m.stream));
     const int64_t* sidx_dev = nullptr;
     if (sidx) {
-        rc = ensure_sample_idx(m, sidx, m.n, false);
+        rc = ensure_sample_idx(m, sidx, m.n, false, n_full);
         if (rc) return rc;
         sidx_dev = m.sample_idx;
     }
@@ -733,7 +899,7 @@ int jxb_decode_packed(jxb_model* h, const uint8_t* packed, size_t bps, size_t ro
     JXB_CUDA_OK(cudaMemcpyAsync(m.packed, packed, rows * bps, cudaMemcpyHostToDevice, m.stream));
     const int64_t* sidx_dev = nullptr;
     if (sidx) {
-        rc = ensure_sample_idx(m, sidx, n, false);
+        rc = ensure_sample_idx(m, sidx, n, false, n_full);
         if (rc) return rc;
         sidx_dev = m.sample_idx;
     }
@@ -781,7 +947,7 @@ int jxb_decode_packed_prepared(jxb_model* h, const uint8_t* packed, size_t bps, 
     JXB_CUDA_OK(cudaMemcpyAsync(m.packed, packed, rows * bps, cudaMemcpyHostToDevice, m.stream));
     const int64_t* sidx_dev = nullptr;
     if (sidx) {
-        rc = ensure_sample_idx(m, sidx, n, false);
+        rc = ensure_sample_idx(m, sidx, n, false, n_full);
         if (rc) return rc;
         sidx_dev = m.sample_idx;
     }
@@ -816,6 +982,12 @@ int jxb_decode_packed_prepared(jxb_model* h, const uint8_t* packed, size_t bps, 
 int jxb_last_stage_ms(jxb_model* h, float ms6[6]) {
     if (!h) return fail(-2, "model is null");
     for (int i = 0; i < 6; ++i) ms6[i] = h->stage_ms[i];
+    return 0;
+}
+
+int jxb_last_stage_ms8(jxb_model* h, float ms8[8]) {
+    if (!h) return fail(-2, "model is null");
+    for (int i = 0; i < 8; ++i) ms8[i] = h->stage_ms[i];
     return 0;
 }
 

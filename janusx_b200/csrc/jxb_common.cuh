@@ -114,6 +114,12 @@ int launch_solve_thread(Model& m, const float* rotT, size_t ldr, size_t max_rows
                         const SolveParams& sp, double* out, int out_cols, int32_t* evals, cudaStream_t st);
 int launch_solve_lane(Model& m, const float* rot, size_t ldc, size_t max_rows, const int32_t* n_rows_dev,
                       const SolveParams& sp, double* out, int out_cols, int32_t* evals, int32_t* queue, cudaStream_t st);
+// streamed scan: solve while later row slabs are still being rotated (k3_solve.cu / cabi.cu scan_streamed)
+int ensure_solve_lane_buffers(Model& m, size_t max_rows, cudaStream_t st);
+int launch_row_ssq_publish(Model& m, const float* rot, size_t ldc, size_t row0, size_t row1, int32_t* sync, cudaStream_t st);
+int launch_solve_lane_stream(Model& m, const float* rot, size_t ldc, size_t rows, const SolveParams& sp, double* out,
+                             int out_cols, int32_t* evals, int32_t* sync, cudaStream_t st);
+int solve_lane_stream_resources(size_t p, int* regs_per_thread, int* smem_per_cta);
 int launch_null_fit(const Model& m, int kind /*0 reml-null(3 out), 1 ml-null brent(2 out), 2 ml at x(1 out)*/,
                     double low, double high, int max_iter, double tol, int has_init, double init,
                     double* out_dev, cudaStream_t st);
@@ -130,5 +136,8 @@ int launch_decode_int8(Model& m, const uint8_t* packed, size_t bps, const int32_
                        const int32_t* counts_by_src, int model_code, cudaStream_t st);
 int launch_rotate_int8_lib(Model& m, size_t rows, bool has_missing, cudaStream_t st);
 int launch_rotate_int8_tc(Model& m, size_t rows, bool has_missing, bool transposed_out, cudaStream_t st);   // k2_i8mma.cu
+int prepare_rotate_tc(Model& m, size_t corr_rows);
+int launch_rotate_int8_tc_slab(Model& m, size_t row0, size_t row1, bool has_missing, bool slim, cudaStream_t st);
+int rotate_slim_resources(int* regs_per_thread, int* smem_per_cta);
 
 }  // namespace jxb

@@ -180,12 +180,14 @@ __global__ void __launch_bounds__(256) decode_center_kernel(const uint8_t* __res
     for (int r = blockIdx.x; r < rows; r += gridDim.x) {
         const int src = src_row ? src_row[r] : r;
         const uint8_t* row = packed + (size_t)src * bps;
-        // decode.rs:218-219: mean_g = (2.0 * maf as f64).max(0.0) as f32; flip is always false on this path
+        // decode.rs:218-219: mean_g = (2.0 * maf as f64).max(0.0) as f32; row_flip (bit 1 of the keep word, set only from
+        // prepared row metadata) reverses the raw LUT to [2, mean_g, 1, 0] (decode.rs:163-178)
         double mg = 2.0 * (double)af_by_src[src];
         if (!(mg > 0.0)) mg = 0.0;
         const float mean_g = (float)mg;
-        const float l0 = model_apply(model, 0.0f), l1 = model_apply(model, mean_g);
-        const float l2 = model_apply(model, 1.0f), l3 = model_apply(model, 2.0f);
+        const bool flip = (counts_by_src[4 * src + 3] & 2) != 0;
+        const float l0 = model_apply(model, flip ? 2.0f : 0.0f), l1 = model_apply(model, mean_g);
+        const float l2 = model_apply(model, 1.0f), l3 = model_apply(model, flip ? 0.0f : 2.0f);
         const int nmiss = counts_by_src[4 * src + 0], nhet = counts_by_src[4 * src + 1];
         const int nhom = counts_by_src[4 * src + 2];
         const int n0 = n - nmiss - nhet - nhom;

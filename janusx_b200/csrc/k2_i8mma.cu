@@ -28,9 +28,12 @@ using namespace tc05;
 
 constexpr int TM = 128;
 constexpr int MSUB = 2;
-constexpr int STAGES = 3;
 constexpr int A_STAGE = MSUB * TM * KSLAB;       // 32 KB
 constexpr int NTHREADS = 192;
+// Two builds of the kernel: the stand-alone one (3 stages = 180 KB of shared memory, registers unconstrained) and the
+// SLIM one that shares an SM with three CTAs of the streamed FP64 solve (cabi.cu scan_streamed): 2 stages (121 KB) and
+// at most 64 registers per thread (192 x 64 = 12 K of the SM's 64 K).
+constexpr int kStagesFull = 3, kStagesSlim = 2;
 constexpr int GROUP_M = 16;
 constexpr int ACC_COLS = 256;                    // TMEM column stride between the two accumulators
 
@@ -48,12 +51,15 @@ __device__ __forceinline__ void tile_coords(int tile, int mt_count, int nt_count
 // mode 0: corr  = coef[2] * T * is        (top slices of the hom indicator; T carries the 256^slice0 factor)
 // mode 1: corr += coef[3] * T * is        (missing indicator)
 // mode 2: rot   = f32(coef[0] * rk + coef[1] * T * is + corr)
-template <int NSL, int CG>
-__global__ void __launch_bounds__(NTHREADS, 1)
+// rows [row0, rows) of the operand planes are rotated (row0 is a multiple of the 256-row CTA tile); `corr` holds the
+// correction terms of these rows only, indexed r - row0.
+template <int NSL, int CG, bool SLIM>
+__global__ void __launch_bounds__(NTHREADS, SLIM ? 5 : 1)
 i8_rotate_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, int a_plane,
-                 int slice0, int mode, int rows, int n, int kslabs, const double* __restrict__ coef,
+                 int slice0, int mode, int row0, int rows, int n, int kslabs, const double* __restrict__ coef,
                  const double* __restrict__ inv_scale, const double* __restrict__ rk, double* __restrict__ corr,
                  size_t ld_corr, float* __restrict__ rot, size_t ldc, int transposed) {
+    constexpr int STAGES = SLIM ? kStagesSlim : kStagesFull;
     constexpr int NB = NSL * CG;                    // MMA N
     constexpr int B_STAGE = NB * KSLAB;
     constexpr int STAGE = A_STAGE + B_STAGE;
@@ -67,7 +73,7 @@ i8_rotate_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const uint32_t tmem_slot = bars + 8 * (2 * STAGES + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    const int mt_count = (rows + MSUB * TM - 1) / (MSUB * TM);
+    const int mt_count = (rows - row0 + MSUB * TM - 1) / (MSUB * TM);
     const int nt_count = (n + CG - 1) / CG;
     const int n_tiles = mt_count * nt_count;
 
@@ -105,8 +111,8 @@ i8_rotate_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     const uint32_t full = bars + 8 * stage;
                     mbar_expect_tx(full, STAGE);
                     const uint32_t sa = tiles_s + stage * STAGE;
-                    tma_load_3d(sa, &tm_a, kb * KSLAB, mt * MSUB * TM, a_plane, full);
-                    tma_load_3d(sa + TM * KSLAB, &tm_a, kb * KSLAB, mt * MSUB * TM + TM, a_plane, full);
+                    tma_load_3d(sa, &tm_a, kb * KSLAB, row0 + mt * MSUB * TM, a_plane, full);
+                    tma_load_3d(sa + TM * KSLAB, &tm_a, kb * KSLAB, row0 + mt * MSUB * TM + TM, a_plane, full);
                     tma_load_3d(sa + A_STAGE, &tm_b, kb * KSLAB, nt * CG, slice0, full);
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
@@ -152,7 +158,7 @@ i8_rotate_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             const int k0 = nt * CG;
 #pragma unroll
             for (int sub = 0; sub < MSUB; ++sub) {
-                const int r = mt * MSUB * TM + sub * TM + quarter * 32 + lane;
+                const int r = row0 + mt * MSUB * TM + sub * TM + quarter * 32 + lane;
                 const bool live = r < rows;
                 double c_a = 0.0, c_t = 0.0;
                 if (live) {
@@ -160,29 +166,37 @@ i8_rotate_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     c_a = cf[0];
                     c_t = mode == 0 ? cf[2] : (mode == 1 ? cf[3] : cf[1]);
                 }
+                double* crow = corr + (size_t)(r - row0) * ld_corr;
                 const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + sub * ACC_COLS;
-#pragma unroll
+#pragma unroll 1
                 for (int cb = 0; cb < CG / 8; ++cb) {
-                    int32_t v[NSL][8];
+                    // Horner over the digit planes, most significant first; the load of plane l-1 is in flight while
+                    // plane l is folded in (two 8-register buffers instead of NSL: the SLIM build has 64 registers)
+                    int32_t v[2][8];
+                    double t[8];
 #pragma unroll
-                    for (int l = 0; l < NSL; ++l) tc_ld8(tbase + l * CG + cb * 8, v[l]);
-                    tc_wait_ld();
+                    for (int j = 0; j < 8; ++j) t[j] = 0.0;
+                    tc_ld8(tbase + (NSL - 1) * CG + cb * 8, v[(NSL - 1) & 1]);
+#pragma unroll
+                    for (int l = NSL - 1; l >= 0; --l) {
+                        tc_wait_ld();
+                        if (l > 0) tc_ld8(tbase + (l - 1) * CG + cb * 8, v[(l - 1) & 1]);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) t[j] = t[j] * 256.0 + (double)v[l & 1][j];
+                    }
                     const int kc = k0 + cb * 8;
                     if (live && kc < n) {
                         double o[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            double t = 0.0;
-#pragma unroll
-                            for (int l = NSL - 1; l >= 0; --l) t = t * 256.0 + (double)v[l][j];
                             const int k = min(kc + j, n - 1);
-                            t *= inv_scale[k];
+                            const double tt = t[j] * inv_scale[k];
                             if (mode == 0) {
-                                o[j] = c_t * (t * 4294967296.0);              // slice0 = 4: 256^4
+                                o[j] = c_t * (tt * 4294967296.0);              // slice0 = 4: 256^4
                             } else if (mode == 1) {
-                                o[j] = corr[(size_t)r * ld_corr + k] + c_t * t;
+                                o[j] = crow[k] + c_t * tt;
                             } else {
-                                o[j] = c_a * rk[k] + c_t * t + corr[(size_t)r * ld_corr + k];
+                                o[j] = c_a * rk[k] + c_t * tt + crow[k];
                             }
                         }
                         if (mode == 2 && transposed) {
@@ -199,7 +213,7 @@ i8_rotate_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                                 for (int j = 0; j < 8 && kc + j < n; ++j) dst[j] = (float)o[j];
                             }
                         } else {
-                            double* dst = corr + (size_t)r * ld_corr + kc;
+                            double* dst = crow + kc;
                             if (kc + 8 <= n) {
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) reinterpret_cast<double2*>(dst)[j] = make_double2(o[2 * j], o[2 * j + 1]);
@@ -225,39 +239,37 @@ i8_rotate_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 }
 
 
-template <int NSL, int CG>
+template <int NSL, int CG, bool SLIM>
 int launch_pass(Model& m, const CUtensorMap& tm_a, const CUtensorMap& tm_b, int a_plane, int slice0, int mode,
-                size_t rows, float* out, size_t ld_out, int transposed, cudaStream_t st) {
+                size_t row0, size_t rows, float* out, size_t ld_out, int transposed, cudaStream_t st) {
     constexpr int STAGE = A_STAGE + NSL * CG * KSLAB;
-    constexpr int SMEM = STAGES * STAGE + 1024 + 256;
+    constexpr int SMEM = (SLIM ? kStagesSlim : kStagesFull) * STAGE + 1024 + 256;
     static bool attr = false;
     if (!attr) {
-        JXB_CUDA_OK(cudaFuncSetAttribute(i8_rotate_kernel<NSL, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        JXB_CUDA_OK(cudaFuncSetAttribute(i8_rotate_kernel<NSL, CG, SLIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        JXB_CUDA_OK(cudaFuncSetAttribute(i8_rotate_kernel<NSL, CG, SLIM>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr = true;
     }
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m.device);
-    const size_t tiles = ((rows + MSUB * TM - 1) / (MSUB * TM)) * ((m.n + CG - 1) / CG);
+    const size_t tiles = ((rows - row0 + MSUB * TM - 1) / (MSUB * TM)) * ((m.n + CG - 1) / CG);
     const int grid = (int)std::min<size_t>((size_t)sms, tiles);
-    i8_rotate_kernel<NSL, CG><<<grid, NTHREADS, SMEM, st>>>(tm_a, tm_b, a_plane, slice0, mode, (int)rows, (int)m.n,
-                                                           (int)(m.ld8 / KSLAB), m.coef, m.q8_inv_scale, m.q8_rk,
-                                                           m.corr64, m.ld_corr, out, ld_out, transposed);
+    i8_rotate_kernel<NSL, CG, SLIM><<<grid, NTHREADS, SMEM, st>>>(tm_a, tm_b, a_plane, slice0, mode, (int)row0, (int)rows,
+                                                                 (int)m.n, (int)(m.ld8 / KSLAB), m.coef, m.q8_inv_scale,
+                                                                 m.q8_rk, m.corr64, m.ld_corr, out, ld_out, transposed);
     note_launch(1);
     JXB_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-}  // namespace
-
-// Hand-written tcgen05 path: pass 2 (hom indicator, top 3 slices) -> [pass M (missing indicator)] -> pass D.
-int launch_rotate_int8_tc(Model& m, size_t rows, bool has_missing, bool transposed_out, cudaStream_t st) {
-    if (rows == 0) return 0;
+// tensor maps of the operand / digit planes and the f64 correction buffer for `corr_rows` rows
+int prepare_rotate_tc_impl(Model& m, size_t corr_rows) {
     const size_t ld_corr = round_up(m.n, 32);
-    if (!m.corr64 || m.corr_rows < m.a8_rows || m.ld_corr != ld_corr) {
-        if (m.corr64) cudaFree(m.corr64);
+    if (!m.corr64 || m.corr_rows < corr_rows || m.ld_corr != ld_corr) {
+        if (m.corr64) { cudaDeviceSynchronize(); cudaFree(m.corr64); }
         m.corr64 = nullptr;
-        JXB_CUDA_OK(cudaMalloc((void**)&m.corr64, m.a8_rows * ld_corr * sizeof(double)));
-        m.corr_rows = m.a8_rows;
+        JXB_CUDA_OK(cudaMalloc((void**)&m.corr64, corr_rows * ld_corr * sizeof(double)));
+        m.corr_rows = corr_rows;
         m.ld_corr = ld_corr;
     }
     if (!m.tmap_a8 || m.tmap_a8_rows != m.a8_rows) {
@@ -273,15 +285,54 @@ int launch_rotate_int8_tc(Model& m, size_t rows, bool has_missing, bool transpos
         if (!rc) rc = encode_planes((CUtensorMap*)m.tmap_q8_3, m.q8, m.ld8, m.q8_rows, 7, 64, 3);
         if (rc) return rc;
     }
+    return 0;
+}
+
+template <bool SLIM>
+int rotate_rows(Model& m, size_t row0, size_t rows, bool has_missing, bool transposed_out, cudaStream_t st) {
     const CUtensorMap& ta = *(const CUtensorMap*)m.tmap_a8;
-    int rc = launch_pass<3, 64>(m, ta, *(const CUtensorMap*)m.tmap_q8_3, /*a_plane=*/1, /*slice0=*/4, /*mode=*/0, rows, m.rot, m.ldc, 0, st);
+    int rc = launch_pass<3, 64, SLIM>(m, ta, *(const CUtensorMap*)m.tmap_q8_3, /*a_plane=*/1, /*slice0=*/4, /*mode=*/0, row0, rows,
+                                      m.rot, m.ldc, 0, st);
     if (!rc && has_missing)
-        rc = launch_pass<7, 32>(m, ta, *(const CUtensorMap*)m.tmap_q8_7, /*a_plane=*/2, 0, /*mode=*/1, rows, m.rot, m.ldc, 0, st);
+        rc = launch_pass<7, 32, SLIM>(m, ta, *(const CUtensorMap*)m.tmap_q8_7, /*a_plane=*/2, 0, /*mode=*/1, row0, rows, m.rot,
+                                      m.ldc, 0, st);
     // transposed: rotT[n][ldr] with ldr = cap_rows shares the rot allocation (cap_rows * ldc >= n * cap_rows floats)
     if (!rc)
-        rc = launch_pass<7, 32>(m, ta, *(const CUtensorMap*)m.tmap_q8_7, /*a_plane=*/0, 0, /*mode=*/2, rows, m.rot,
-                                transposed_out ? m.cap_rows : m.ldc, transposed_out ? 1 : 0, st);
+        rc = launch_pass<7, 32, SLIM>(m, ta, *(const CUtensorMap*)m.tmap_q8_7, /*a_plane=*/0, 0, /*mode=*/2, row0, rows, m.rot,
+                                      transposed_out ? m.cap_rows : m.ldc, transposed_out ? 1 : 0, st);
     return rc;
+}
+
+}  // namespace
+
+int prepare_rotate_tc(Model& m, size_t corr_rows) { return prepare_rotate_tc_impl(m, corr_rows); }
+
+// Hand-written tcgen05 path: pass 2 (hom indicator, top 3 slices) -> [pass M (missing indicator)] -> pass D.
+int launch_rotate_int8_tc(Model& m, size_t rows, bool has_missing, bool transposed_out, cudaStream_t st) {
+    if (rows == 0) return 0;
+    int rc = prepare_rotate_tc(m, m.a8_rows);
+    if (rc) return rc;
+    return rotate_rows<false>(m, 0, rows, has_missing, transposed_out, st);
+}
+
+// Row slab [row0, row1) of the decoded batch -> rows [row0, row1) of m.rot (row-major); row0 must be a multiple of 256.
+// The correction buffer (prepare_rotate_tc) only needs row1 - row0 rows.  slim: the build that shares an SM with the
+// streamed solve (2 stages, <= 64 registers).
+int launch_rotate_int8_tc_slab(Model& m, size_t row0, size_t row1, bool has_missing, bool slim, cudaStream_t st) {
+    if (row1 <= row0) return 0;
+    if (row0 % (MSUB * TM)) return fail(-2, "rotation slabs must start at a multiple of 256 rows");
+    if (m.corr_rows < row1 - row0) return fail(-2, "rotation correction buffer is smaller than the slab");
+    return slim ? rotate_rows<true>(m, row0, row1, has_missing, false, st) : rotate_rows<false>(m, row0, row1, has_missing, false, st);
+}
+
+// registers per thread / shared memory per CTA of the SLIM pass-D kernel (the larger of the slim instantiations)
+int rotate_slim_resources(int* regs, int* smem) {
+    cudaFuncAttributes f7, f3;
+    if (cudaFuncGetAttributes(&f7, i8_rotate_kernel<7, 32, true>) != cudaSuccess) return -1;
+    if (cudaFuncGetAttributes(&f3, i8_rotate_kernel<3, 64, true>) != cudaSuccess) return -1;
+    *regs = std::max(f7.numRegs, f3.numRegs);
+    *smem = (int)std::max(f7.sharedSizeBytes, f3.sharedSizeBytes) + kStagesSlim * (A_STAGE + 7 * 32 * KSLAB) + 1024 + 256;
+    return 0;
 }
 
 }  // namespace jxb

@@ -111,8 +111,9 @@ __global__ void __launch_bounds__(256) decode_int8_kernel(const uint8_t* __restr
             double mg = 2.0 * (double)af_by_src[src];
             if (!(mg > 0.0)) mg = 0.0;
             const float mean_g = (float)mg;
-            const float l0 = model_apply8(model, 0.0f), l1 = model_apply8(model, mean_g);
-            const float l2 = model_apply8(model, 1.0f), l3 = model_apply8(model, 2.0f);
+            const bool flip = (counts_by_src[4 * src + 3] & 2) != 0;     // prepared row_flip: LUT [2, mean_g, 1, 0]
+            const float l0 = model_apply8(model, flip ? 2.0f : 0.0f), l1 = model_apply8(model, mean_g);
+            const float l2 = model_apply8(model, 1.0f), l3 = model_apply8(model, flip ? 0.0f : 2.0f);
             const int nmiss = counts_by_src[4 * src + 0], nhet = counts_by_src[4 * src + 1];
             const int nhom = counts_by_src[4 * src + 2];
             const int n0 = n - nmiss - nhet - nhom;

@@ -72,6 +72,35 @@ int JXB_CAT(k3_launch_solve_lane_p, JXB_P)(const k3::ModelView& mv, int sms, con
     return 0;
 }
 
+// Streamed (co-resident) lane kernel: 3 CTAs per SM, 16-sample tiles.  `sync` = {queue, ready, abort} (zeroed by the caller).
+int JXB_CAT(k3_launch_solve_lane_stream_p, JXB_P)(const k3::ModelView& mv, int sms, const float* rot, size_t ldc,
+                                                  int max_rows, const SolveParams& sp, double* out, int out_cols,
+                                                  int32_t* evals, const void* log_table, const double* ssq,
+                                                  int32_t* sync, cudaStream_t st) {
+    constexpr int kSmem = 4 * (int)sizeof(k3::ThreadTile<JXB_P, 16>);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k3::solve_lane_stream_kernel<JXB_P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+        // same (maximum) shared-memory carve-out as the rotation kernel it shares SMs with: an SM cannot change its
+        // L1/shared split while CTAs of another kernel are resident
+        cudaFuncSetAttribute(k3::solve_lane_stream_kernel<JXB_P>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        attr = true;
+    }
+    const int blocks = std::min((max_rows + 127) / 128, sms * 3);
+    k3::solve_lane_stream_kernel<JXB_P><<<blocks, 128, kSmem, st>>>(mv, rot, ldc, max_rows, sp, out, out_cols, evals,
+                                                                   (const k3::LogTable*)log_table, ssq, sync);
+    return 0;
+}
+
+// registers per thread and shared memory per CTA (static + dynamic) of the streamed kernel, for the co-residency check
+int JXB_CAT(k3_solve_lane_stream_res_p, JXB_P)(int* regs, int* smem) {
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, k3::solve_lane_stream_kernel<JXB_P>) != cudaSuccess) return -1;
+    *regs = fa.numRegs;
+    *smem = (int)fa.sharedSizeBytes + 4 * (int)sizeof(k3::ThreadTile<JXB_P, 16>);
+    return 0;
+}
+
 int JXB_CAT(k3_launch_null_p, JXB_P)(const k3::ModelView& mv, int kind, double low, double high, int max_iter,
                                      double tol, int has_init, double init, double* out_dev, cudaStream_t st) {
     constexpr int kSmem = JXB_K3_BUFS * k3::WarpDims<JXB_P, false>::SMEM_DOUBLES * (int)sizeof(double);

@@ -14,7 +14,10 @@ namespace jxb {
                                     const SolveParams&, double*, int, int32_t*, const void*, cudaStream_t);    \
     int k3_launch_solve_lane_p##P(const k3::ModelView&, int, const float*, size_t, int, const int32_t*,        \
                                   const SolveParams&, double*, int, int32_t*, const void*, double*, int32_t*,  \
-                                  cudaStream_t);
+                                  cudaStream_t);                                                               \
+    int k3_launch_solve_lane_stream_p##P(const k3::ModelView&, int, const float*, size_t, int, const SolveParams&, \
+                                         double*, int, int32_t*, const void*, const double*, int32_t*, cudaStream_t); \
+    int k3_solve_lane_stream_res_p##P(int*, int*);
 JXB_DECL_P(1) JXB_DECL_P(2) JXB_DECL_P(3) JXB_DECL_P(4) JXB_DECL_P(5) JXB_DECL_P(6) JXB_DECL_P(7) JXB_DECL_P(8)
 #undef JXB_DECL_P
 
@@ -148,6 +151,56 @@ int launch_solve_lane(Model& m, const float* rot, size_t ldc, size_t max_rows, c
 #undef L_DYN
     JXB_CUDA_OK(cudaGetLastError());
     return 0;
+}
+
+// ---- streamed scan (cabi.cu scan_streamed): the solve runs while later row slabs are still being rotated ----------
+int ensure_solve_lane_buffers(Model& m, size_t max_rows, cudaStream_t st) {
+    { int rc = ensure_log_table(m, st); if (rc) return rc; }
+    if (m.ssq_cap < max_rows) {
+        JXB_CUDA_OK(cudaStreamSynchronize(st));
+        if (m.ssq) cudaFree(m.ssq);
+        m.ssq = nullptr;
+        JXB_CUDA_OK(cudaMalloc((void**)&m.ssq, std::max(max_rows, m.cap_rows) * sizeof(double)));
+        m.ssq_cap = std::max(max_rows, m.cap_rows);
+    }
+    return 0;
+}
+
+// sums of squares of rows [row0, row1) of the row-major rotated block, then publish `row1` rows as ready
+int launch_row_ssq_publish(Model& m, const float* rot, size_t ldc, size_t row0, size_t row1, int32_t* sync, cudaStream_t st) {
+    if (row1 > row0) {
+        const int blocks = (int)std::min<size_t>((row1 - row0 + 7) / 8, (size_t)sm_count(m.device) * 8);
+        row_ssq_kernel<<<blocks, 256, 0, st>>>(rot, ldc, (int)m.n, (int)row1, nullptr, m.ssq, (int)row0);
+    }
+    publish_ready_kernel<<<1, 1, 0, st>>>(sync, (int)row1);
+    JXB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_solve_lane_stream(Model& m, const float* rot, size_t ldc, size_t rows, const SolveParams& sp, double* out,
+                             int out_cols, int32_t* evals, int32_t* sync, cudaStream_t st) {
+    if (rows == 0) return 0;
+    if (m.p < 1 || m.p > 4) return fail(-2, "streamed lane solve supports 1..4 covariate columns");
+    const ModelView mv = view_of(m);
+    const int sms = sm_count(m.device);
+    switch (m.p) {
+        case 1: k3_launch_solve_lane_stream_p1(mv, sms, rot, ldc, (int)rows, sp, out, out_cols, evals, m.log_table, m.ssq, sync, st); break;
+        case 2: k3_launch_solve_lane_stream_p2(mv, sms, rot, ldc, (int)rows, sp, out, out_cols, evals, m.log_table, m.ssq, sync, st); break;
+        case 3: k3_launch_solve_lane_stream_p3(mv, sms, rot, ldc, (int)rows, sp, out, out_cols, evals, m.log_table, m.ssq, sync, st); break;
+        default: k3_launch_solve_lane_stream_p4(mv, sms, rot, ldc, (int)rows, sp, out, out_cols, evals, m.log_table, m.ssq, sync, st); break;
+    }
+    JXB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int solve_lane_stream_resources(size_t p, int* regs, int* smem) {
+    switch (p) {
+        case 1: return k3_solve_lane_stream_res_p1(regs, smem);
+        case 2: return k3_solve_lane_stream_res_p2(regs, smem);
+        case 3: return k3_solve_lane_stream_res_p3(regs, smem);
+        case 4: return k3_solve_lane_stream_res_p4(regs, smem);
+        default: return -1;
+    }
 }
 
 int launch_null_fit(const Model& m, int kind, double low, double high, int max_iter, double tol, int has_init,

@@ -285,10 +285,21 @@ class DeviceModel:
                                    C.byref(nk)))
         return keep.astype(bool), af, missing, out[: nk.value], ev[: nk.value]
 
+    def scan_fetch_dev(self, rows: int, cols: int, out_dst_ptr=None, af_dst_ptr=None, counts_dst_ptr=None) -> int:
+        """Copy the last scan's results device-to-device (out f64[n_kept, cols] compacted; af f32[rows]; counts
+        i32[rows, 4] by source row) and return n_kept."""
+        nk = C.c_size_t()
+        check(lib().jxb_scan_fetch_dev(self.handle, rows, cols, out_dst_ptr, af_dst_ptr, counts_dst_ptr, C.byref(nk)))
+        return int(nk.value)
+
     def stage_ms(self):
-        ms = (C.c_float * 6)()
-        check(lib().jxb_last_stage_ms(self.handle, ms))
-        return dict(zip(("count_qc", "decode", "rotate", "solve", "h2d", "d2h"), [float(v) for v in ms]))
+        """Device timers of the last scan (ms).  Streamed scans (`streamed` = 1): `rotate` covers all rotation slabs with
+        the solve running underneath, `solve` is what was left of the solve afterwards, `solve_kernel` the solve
+        kernel's own duration on its stream."""
+        ms = (C.c_float * 8)()
+        check(lib().jxb_last_stage_ms8(self.handle, ms))
+        return dict(zip(("count_qc", "decode", "rotate", "solve", "h2d", "d2h", "solve_kernel", "streamed"),
+                        [float(v) for v in ms]))
 
     # -- file level -------------------------------------------------------------------------------
     def scan_bed_to_tsv(self, bed_prefix, out_tsv, maf_thr, miss_thr, het_thr, genetic_model="add", snps_only=False,
@@ -407,6 +418,12 @@ def set_thread_solve_min_rows(rows: int) -> None:
 def set_big_solve_kernel(variant: int) -> None:
     """Large-batch solve kernel: 0 = lane-per-SNP with refill (default), 1 = thread-per-SNP on an SNP-minor block."""
     lib().jxb_set_big_solve_kernel(int(variant))
+
+
+def set_stream_overlap(on: bool, slab_rows: int = 0) -> None:
+    """Streamed scan (default on): rotate large batches in slabs while one persistent solve kernel consumes the rotated
+    rows, so the tensor pipe and the FP64 pipe run concurrently.  slab_rows = 0 keeps the current slab size (8192)."""
+    lib().jxb_set_stream_overlap(1 if on else 0, int(slab_rows))
 
 
 def clear_model_cache() -> None:

@@ -26,11 +26,33 @@ _lib = None
 MODEL_CODES = {"add": 0, "dom": 1, "rec": 2, "het": 3}
 
 
+def _host_key() -> str:
+    """-march=native binds the library to the CPU it was built on: a copy that travelled to another host is rebuilt."""
+    model, flags = "", ""
+    try:
+        with open("/proc/cpuinfo") as fh:
+            for line in fh:
+                if line.startswith("model name") and not model:
+                    model = line.split(":", 1)[1].strip()
+                elif line.startswith("flags") and not flags:
+                    flags = line.split(":", 1)[1].strip()
+                if model and flags:
+                    break
+    except OSError:
+        pass
+    import hashlib
+    return hashlib.sha1((model + "|" + flags + "|" + (_HERE / "Makefile").read_text()).encode()).hexdigest()
+
+
 def build(force: bool = False) -> Path:
-    """Compile the oracle with the committed Makefile (gcc, -ffp-contract=off)."""
+    """Compile the oracle with the committed Makefile (gcc -O3 -march=native -ffp-contract=off)."""
     src_m = max((_HERE / "jx_oracle.c").stat().st_mtime, (_HERE / "jx_oracle.h").stat().st_mtime)
-    if force or not _LIB_PATH.exists() or _LIB_PATH.stat().st_mtime < src_m:
-        subprocess.run(["make", "-C", str(_HERE)], check=True, capture_output=True)
+    stamp = _HERE / "_build" / "host.key"
+    key = _host_key()
+    stale = not _LIB_PATH.exists() or _LIB_PATH.stat().st_mtime < src_m or not stamp.exists() or stamp.read_text() != key
+    if force or stale:
+        subprocess.run(["make", "-B", "-C", str(_HERE)], check=True, capture_output=True)
+        stamp.write_text(key)
     return _LIB_PATH
 
 

@@ -70,6 +70,31 @@ def test_format_row_matches_oracle(cabi, oracle):
         assert buf.raw[:n] == oracle.format_row("7", 1000 + i, snp, "A", "TG", float(af), float(mr), a), (i, r)
 
 
+def test_tsv_formatter_long_alleles_never_overflow(cabi, oracle):
+    """BIM alleles have no length limit (indels, SVs; vcf_cache.cpp copies REF/ALT verbatim) and Rust formats rows into a
+    String.  A buffer below the worst case is refused with the size to retry with; a big one holds the full row."""
+    a = np.array([0.5, 0.25, 6.1e-5], dtype=np.float64)
+    short = oracle.format_row("7", 12, "rs1", "A", "T", 0.25, 0.5, a)
+    for alen in (1900, 3000, 5000, 70000):
+        allele = ("ACGT" * (alen // 4 + 1))[:alen].encode()
+        small = C.create_string_buffer(2048)
+        need = cabi.lib().jxb_format_row(small, 2048, b"7", 12, b"rs1", b"A", allele, np.float32(0.25), np.float32(0.5),
+                                         a.ctypes.data_as(C.POINTER(C.c_double)), 3)
+        assert need > 2048
+        big = C.create_string_buffer(need)
+        n = cabi.lib().jxb_format_row(big, need, b"7", 12, b"rs1", b"A", allele, np.float32(0.25), np.float32(0.5),
+                                      a.ctypes.data_as(C.POINTER(C.c_double)), 3)
+        assert n <= need
+        assert big.raw[:n] == short.replace(b"\tA\tT\t", b"\tA\t" + allele + b"\t")
+    # huge finite values: `{:.4}` of 1e300 is 306 characters per field
+    h = np.array([1e300, 1e300, 0.5, 1e300, -1e300, 0.5], dtype=np.float64)
+    buf = C.create_string_buffer(8192)
+    n = cabi.lib().jxb_format_row(buf, 8192, b"1", 1, b"s", b"A", b"C", np.float32(0.1), np.float32(0.0),
+                                  h.ctypes.data_as(C.POINTER(C.c_double)), 6)
+    f = buf.raw[:n].split(b"\t")
+    assert len(f) == 14 and f[7] == (b"%.4f" % 1e300) and f[-1] == b"5.0000e-1\n"
+
+
 def test_tsv_writer_blocks_match_oracle_rows(cabi, oracle, tmp_path):
     """GwasAssocTsvWriter (assoc2tsv.rs:765-892): header by schema, verbatim SNP names, allele strings by model."""
     from janusx_b200 import jxrs
