@@ -271,7 +271,7 @@ def measure_int8_peak(torch, device, n):
     k = (n + 7) // 8 * 8
     try:
         a = torch.randint(-3, 3, (m, k), dtype=torch.int8, device=device)
-        b = torch.randint(-100, 100, (k, k), dtype=torch.int8, device=device)
+        b = torch.randint(-100, 100, (k, k), dtype=torch.int8, device=device).T   # column-major B: the "TN" layout IMMA wants
         best = 0.0
         for i in range(6):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

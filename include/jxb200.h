@@ -121,6 +121,32 @@ int jxb_scan_packed(jxb_model* m, const uint8_t* packed_host, size_t bytes_per_s
                     const int64_t* sample_idx_host, const uint8_t* pre_keep_host, const jxb_qc_cfg* qc,
                     const jxb_solve_cfg* cfg, int mode, uint8_t* keep_host, float* af_host, int32_t* missing_host,
                     double* out_host, int32_t* evals_host, size_t* n_kept_host);
+/* Same with prepared row metadata (src/stats/lmm.rs:1237-1262, 3040-3187): row_af_host f32[rows] (nullable) replaces the
+ * allele frequency counted on the device -- it is the imputation mean 2*row_maf the reference decodes with
+ * (src/decode/decode.rs:213-219), whatever samples it was computed over, and the value returned in af_host;
+ * row_flip_host u8[rows] (nullable) reverses the code LUT to [2, mean, 1, 0] (decode.rs:163-178).  The QC thresholds
+ * in `qc` still apply to the device counts; callers with trusted metadata pass maf 0, miss 1, het 0. */
+int jxb_scan_packed_prepared(jxb_model* m, const uint8_t* packed_host, size_t bytes_per_snp, size_t rows, size_t n_full,
+                             const int64_t* sample_idx_host, const uint8_t* pre_keep_host, const float* row_af_host,
+                             const uint8_t* row_flip_host, const jxb_qc_cfg* qc, const jxb_solve_cfg* cfg, int mode,
+                             uint8_t* keep_host, float* af_host, int32_t* missing_host, double* out_host,
+                             int32_t* evals_host, size_t* n_kept_host);
+/* Double-buffered input staging -- the reference's producer/consumer double buffer (src/io/pipeline.rs:47-92) on the
+ * device side: the library keeps two packed-row buffers in HBM and a copy stream.
+ *   jxb_stage_packed       asynchronous H2D of the NEXT batch (pinned host memory for a truly asynchronous copy) into
+ *                          the idle buffer; returns at once.  One batch may be staged at a time.
+ *   jxb_scan_staged_begin  the staged batch becomes the current one (the compute stream waits for its copy; the buffers
+ *                          swap), which frees the idle buffer for the next jxb_stage_packed.
+ *   jxb_scan_staged        jxb_scan_packed_prepared on the current batch (no H2D of packed rows inside).
+ * Loop: stage(0); for i: begin(); stage(i+1); scan_staged(i) -- batch i+1 goes up while batch i computes.
+ *   jxb_stage_cancel       drops a staged / current batch (error paths). */
+int jxb_stage_packed(jxb_model* m, const uint8_t* packed_host, size_t bytes_per_snp, size_t rows);
+int jxb_scan_staged_begin(jxb_model* m);
+int jxb_scan_staged(jxb_model* m, size_t n_full, const int64_t* sample_idx_host, const uint8_t* pre_keep_host,
+                    const float* row_af_host, const uint8_t* row_flip_host, const jxb_qc_cfg* qc, const jxb_solve_cfg* cfg,
+                    int mode, uint8_t* keep_host, float* af_host, int32_t* missing_host, double* out_host,
+                    int32_t* evals_host, size_t* n_kept_host);
+void jxb_stage_cancel(jxb_model* m);
 /* Same with the packed batch already in HBM (bench.py `value`; multi-GPU shards).  Results stay on the
  * device in the model workspace; fetch with jxb_scan_fetch.  Asynchronous on the model's stream. */
 int jxb_scan_packed_dev(jxb_model* m, const uint8_t* packed_dev, size_t bytes_per_snp, size_t rows, size_t n_full,
@@ -203,6 +229,15 @@ typedef struct {
      * allele frequency and missingness are recomputed from the packed rows on the device. */
     const int64_t* row_indices;
     size_t n_row_indices;
+    /* the rest of the prepared metadata, each nullable, n_row_indices entries parallel to row_indices: row_maf = the
+     * imputation frequency and the TSV af column; row_flip reverses the code LUT; row_missing = missing RATE, turned
+     * into a count by round(rate * n) and back into the TSV miss column (src/stats/lmm.rs:1934-1950, 2576-2612) */
+    const float* row_maf;
+    const uint8_t* row_flip;
+    const float* row_missing;
+    /* host staging (src/io/pipeline.rs:47-92, src/io/gload.rs:523-800): 0 = default.  The BED payload is copied in
+     * windows of at most this many MiB through a pinned double buffer, batch i+1 going up while batch i computes. */
+    size_t mmap_window_mb;
 } jxb_bed_scan_cfg;
 int jxb_scan_bed_to_tsv(jxb_model* m, const jxb_bed_scan_cfg* cfg, size_t* rows_written, jxb_progress_cb cb,
                         void* user);

@@ -40,7 +40,9 @@ class BedScanCfg(C.Structure):
                 ("mode", C.c_int32), ("snps_only", C.c_int32), ("sample_ids", C.POINTER(C.c_char_p)),
                 ("n_sample_ids", C.c_size_t), ("batch_rows", C.c_size_t), ("snp_begin", C.c_size_t),
                 ("snp_end", C.c_size_t), ("write_header", C.c_int32), ("progress_every", C.c_size_t),
-                ("row_indices", C.POINTER(C.c_int64)), ("n_row_indices", C.c_size_t)]
+                ("row_indices", C.POINTER(C.c_int64)), ("n_row_indices", C.c_size_t),
+                ("row_maf", C.POINTER(C.c_float)), ("row_flip", C.POINTER(C.c_uint8)),
+                ("row_missing", C.POINTER(C.c_float)), ("mmap_window_mb", C.c_size_t)]
 
 
 # every symbol include/jxb200.h declares: (name, restype, argtypes or None)
@@ -72,6 +74,13 @@ SYMBOLS = {
     "jxb_rotate_block_f32": (C.c_int, [_vp, _vp, C.c_size_t, _vp, C.c_int]),
     "jxb_scan_packed": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_size_t, _vp, _vp, C.POINTER(QcCfg),
                                   C.POINTER(SolveCfg), C.c_int, _vp, _vp, _vp, _vp, _vp, _psz]),
+    "jxb_scan_packed_prepared": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_size_t, _vp, _vp, _vp, _vp,
+                                           C.POINTER(QcCfg), C.POINTER(SolveCfg), C.c_int, _vp, _vp, _vp, _vp, _vp, _psz]),
+    "jxb_stage_packed": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t]),
+    "jxb_scan_staged_begin": (C.c_int, [_vp]),
+    "jxb_scan_staged": (C.c_int, [_vp, C.c_size_t, _vp, _vp, _vp, _vp, C.POINTER(QcCfg), C.POINTER(SolveCfg), C.c_int,
+                                  _vp, _vp, _vp, _vp, _vp, _psz]),
+    "jxb_stage_cancel": (None, [_vp]),
     "jxb_scan_packed_dev": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_size_t, _vp, C.POINTER(QcCfg),
                                       C.POINTER(SolveCfg), C.c_int]),
     "jxb_scan_fetch": (C.c_int, [_vp, C.c_size_t, C.c_int, _vp, _vp, _vp, _vp, _vp, _psz]),

@@ -7,8 +7,12 @@
 //   AsyncTsvWriter (writer thread)                                 src/stats/common.rs:374-468
 //   resolve_snp_name                                               src/stats/lmm.rs:1952-1958
 //
-// The device work of each batch is jxb_scan_packed (K1 -> K2 -> K3).  A writer thread formats and
-// writes batch i while the GPU runs batch i+1 (the reference's double buffer, src/io/pipeline.rs:49-92).
+// The device work of each batch is jxb_scan_staged (K1 -> K2 -> K3).  Three stages overlap, like the reference's
+// double buffer (src/io/pipeline.rs:47-92): a producer thread parses the BIM rows of batch i+2 and copies its packed
+// rows from the memory-mapped BED into a pinned ring slot; batch i+1 goes up to the second device buffer on a copy
+// stream (jxb_stage_packed) while batch i computes; a writer thread formats and writes batch i-1.  The ring is the
+// only host memory that scales with the batch, and `mmap_window_mb` (the CLI's -mem) bounds it
+// (WindowedBedMatrix, src/io/gload.rs:523-800).
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -29,6 +33,8 @@
 #include <thread>
 #include <unordered_map>
 #include <vector>
+
+#include <cuda_runtime.h>
 
 #include "../../include/jxb200.h"
 
@@ -463,7 +469,25 @@ extern "C" int jxb_scan_bed_to_tsv(jxb_model* m, const jxb_bed_scan_cfg* cfg, si
         qc.maf_thr = 0.0f; qc.miss_thr = 1.0f; qc.het_thr = 0.0f;
     }
     const size_t total = prepared ? cfg->n_row_indices : end - begin;
-    const size_t step = std::max<size_t>(1, std::min<size_t>(cfg->batch_rows ? cfg->batch_rows : 4096, std::max<size_t>(total, 1)));
+    size_t step = std::max<size_t>(1, std::min<size_t>(cfg->batch_rows ? cfg->batch_rows : 4096, std::max<size_t>(total, 1)));
+    // pinned ring of kRing batch-sized slots: with a -mem window the batch shrinks so that the ring fits it
+    constexpr int kRing = 3;
+    if (cfg->mmap_window_mb) {
+        const size_t budget = (cfg->mmap_window_mb << 20) / kRing / bps;
+        step = std::max<size_t>(256, std::min(step, budget));
+    }
+    const size_t span_max = prepared ? std::min(step, end - begin) : std::min(step, std::max<size_t>(total, 1));
+    uint8_t* ring[kRing] = {nullptr, nullptr, nullptr};
+    bool ring_free[kRing] = {true, true, true};
+    for (int k = 0; k < kRing; ++k) {
+        if (cudaHostAlloc((void**)&ring[k], std::max<size_t>(span_max * bps, 16), cudaHostAllocPortable) != cudaSuccess) {
+            (void)cudaGetLastError();
+            for (int j = 0; j < k; ++j) cudaFreeHost(ring[j]);
+            wr.finish(); fclose(wr.fp); unmap();
+            return fail(-36, "pinned staging ring: cudaHostAlloc of " + std::to_string(span_max * bps) + " bytes failed");
+        }
+    }
+    auto free_ring = [&]() { for (int k = 0; k < kRing; ++k) if (ring[k]) { cudaFreeHost(ring[k]); ring[k] = nullptr; } };
     size_t next_emit = cfg->progress_every ? std::max<size_t>(1, std::min(cfg->progress_every, total)) : 0;
     // Producer thread (the reference's producer, src/io/pipeline.rs:49-92): parses the BIM rows of the next batches and
     // builds their masks while the device scans the current one; errors travel with the item and are raised on the
@@ -472,7 +496,11 @@ extern "C" int jxb_scan_bed_to_tsv(jxb_model* m, const jxb_bed_scan_cfg* cfg, si
         Batch* b = nullptr;
         size_t c0 = 0, rows = 0, listed = 0;
         std::vector<uint8_t> mask;
+        std::vector<float> row_af;        // prepared metadata of the listed rows (by row of this batch)
+        std::vector<uint8_t> row_flip;
+        std::vector<int32_t> row_miss;    // missing COUNT recovered from the caller's rate; -1 = not listed
         bool has_mask = false, last = false;
+        int slot = -1;                    // pinned ring slot holding this batch's packed rows
         int code = 0;
         std::string msg;
     };
@@ -537,8 +565,19 @@ extern "C" int jxb_scan_bed_to_tsv(jxb_model* m, const jxb_bed_scan_cfg* cfg, si
                 it->has_mask = true;
                 it->mask.assign(rows, prepared ? 0 : 1);
                 if (prepared) {
+                    if (cfg->row_maf) it->row_af.assign(rows, 0.0f);
+                    if (cfg->row_flip) it->row_flip.assign(rows, 0);
+                    if (cfg->row_missing) it->row_miss.assign(rows, -1);
                     while (list_pos < cfg->n_row_indices && (size_t)cfg->row_indices[list_pos] < c0 + rows) {
-                        it->mask[(size_t)cfg->row_indices[list_pos] - c0] = 1;
+                        const size_t r = (size_t)cfg->row_indices[list_pos] - c0;
+                        it->mask[r] = 1;
+                        if (cfg->row_maf) it->row_af[r] = cfg->row_maf[list_pos];
+                        if (cfg->row_flip) it->row_flip[r] = cfg->row_flip[list_pos] ? 1 : 0;
+                        if (cfg->row_missing) {
+                            // missing_count_from_rate, src/stats/lmm.rs:1934-1940
+                            const float v = cfg->row_missing[list_pos];
+                            it->row_miss[r] = (!std::isfinite(v) || v <= 0.0f) ? 0 : (int32_t)std::max(0.0, std::round((double)v * (double)n));
+                        }
                         ++list_pos;
                         ++it->listed;
                     }
@@ -547,6 +586,14 @@ extern "C" int jxb_scan_bed_to_tsv(jxb_model* m, const jxb_bed_scan_cfg* cfg, si
                     for (size_t r = 0; r < rows; ++r)
                         if (!simple_snp_allele(b->sites[r].a0) || !simple_snp_allele(b->sites[r].a1)) it->mask[r] = 0;
             }
+            // packed rows of the batch: mmap (page cache / disk) -> a free pinned ring slot
+            {
+                std::unique_lock<std::mutex> lk(pmu);
+                pcv.wait(lk, [&] { return stop || ring_free[0] || ring_free[1] || ring_free[2]; });
+                if (stop) { delete b; delete it; return; }
+                for (int k = 0; k < kRing; ++k) if (ring_free[k]) { it->slot = k; ring_free[k] = false; break; }
+            }
+            memcpy(ring[it->slot], payload + c0 * bps, rows * bps);
             if (!emit(it)) return;
             c0 += rows;
         }
@@ -564,33 +611,57 @@ extern "C" int jxb_scan_bed_to_tsv(jxb_model* m, const jxb_bed_scan_cfg* cfg, si
 
     int rc = 0;
     size_t scanned = 0;
-    for (;;) {
+    auto pop = [&]() {
         Prep* it = nullptr;
-        {
-            std::unique_lock<std::mutex> lk(pmu);
-            pcv.wait(lk, [&] { return !pq.empty(); });
-            it = pq.front();
-            pq.pop_front();
-        }
+        std::unique_lock<std::mutex> lk(pmu);
+        pcv.wait(lk, [&] { return !pq.empty(); });
+        it = pq.front();
+        pq.pop_front();
+        lk.unlock();
         pcv.notify_all();
-        if (it->last) {
-            if (it->code) rc = fail(it->code, it->msg);
-            delete it;
-            break;
+        return it;
+    };
+    auto release_slot = [&](Prep* it) {
+        if (it && it->slot >= 0) {
+            { std::lock_guard<std::mutex> lk(pmu); ring_free[it->slot] = true; }
+            it->slot = -1;
+            pcv.notify_all();
         }
-        Batch* b = it->b;
-        rc = jxb_scan_packed(m, payload + it->c0 * bps, bps, it->rows, n_full, identity ? nullptr : sidx.data(),
-                             it->has_mask ? it->mask.data() : nullptr, &qc, &solve, mode, b->keep.data(), b->af.data(),
-                             b->missing.data(), b->out.data(), nullptr, &b->n_kept);
-        if (rc) { delete b; delete it; break; }
+    };
+    auto drop = [&](Prep* it) { if (it) { release_slot(it); if (it->b) delete it->b; delete it; } };
+    // cur = the batch on the device; nxt = the batch going up while cur computes
+    Prep* cur = pop();
+    if (!cur->last) rc = jxb_stage_packed(m, ring[cur->slot], bps, cur->rows);
+    while (!rc && !cur->last) {
+        Prep* nxt = pop();
+        Batch* b = cur->b;
+        // jxb_scan_staged waits for cur's copy and makes it the working buffer; nxt is staged right after the swap is
+        // ordered, i.e. from inside the same call sequence: stage it first into the OTHER buffer -- the library keeps
+        // two device buffers and swaps them at every scan
+        rc = jxb_scan_staged_begin(m);
+        if (!rc && !nxt->last) rc = jxb_stage_packed(m, ring[nxt->slot], bps, nxt->rows);
+        if (!rc)
+            rc = jxb_scan_staged(m, n_full, identity ? nullptr : sidx.data(), cur->has_mask ? cur->mask.data() : nullptr,
+                                 cur->row_af.empty() ? nullptr : cur->row_af.data(),
+                                 cur->row_flip.empty() ? nullptr : cur->row_flip.data(), &qc, &solve, mode, b->keep.data(),
+                                 b->af.data(), b->missing.data(), b->out.data(), nullptr, &b->n_kept);
+        if (rc) { drop(nxt); break; }
+        if (!cur->row_miss.empty())
+            for (size_t r = 0; r < cur->rows; ++r)
+                if (cur->row_miss[r] >= 0) b->missing[r] = cur->row_miss[r];
         wr.push(b);
-        scanned += prepared ? it->listed : it->rows;
-        delete it;
+        cur->b = nullptr;
+        scanned += prepared ? cur->listed : cur->rows;
+        drop(cur);
+        cur = nxt;
         if (cb && next_emit && scanned >= next_emit) {
             if (cb(scanned < total ? scanned : total, total, user) != 0) { rc = fail(-40, "interrupted by progress callback"); break; }
             next_emit = std::min((scanned / cfg->progress_every + 1) * cfg->progress_every, total);
         }
     }
+    if (!rc && cur->last && cur->code) rc = fail(cur->code, cur->msg);
+    drop(cur);
+    jxb_stage_cancel(m);
     {
         // stop the producer (no-op when it already delivered its last item) and drop what it had queued
         std::lock_guard<std::mutex> lk(pmu);
@@ -600,6 +671,7 @@ extern "C" int jxb_scan_bed_to_tsv(jxb_model* m, const jxb_bed_scan_cfg* cfg, si
     producer.join();
     for (Prep* it : pq) { if (it->b) delete it->b; delete it; }
     pq.clear();
+    free_ring();
     if (rc == 0 && cb) cb(total, total, user);
     wr.finish();
     const bool ioerr = wr.io_error || fclose(wr.fp) != 0;

@@ -22,6 +22,13 @@ struct jxb_model {
     // streamed scan: the solve runs on stream2 while m.stream still rotates later row slabs
     cudaStream_t stream2 = nullptr;
     cudaEvent_t ev_slab0 = nullptr, ev_solve = nullptr;
+    // double-buffered input staging (jxb_stage_packed / jxb_scan_staged): batch i+1 goes up on copy_stream while batch i computes
+    uint8_t* packed2 = nullptr;
+    size_t packed2_bytes = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copy = nullptr;
+    size_t staged_rows = 0, staged_bps = 0, cur_rows = 0, cur_bps = 0;
+    bool staged = false, cur_valid = false;
     bool last_streamed = false;
     size_t last_nk = 0;           // kept rows of the last scan (known on the host after the decode stage)
     double* scal = nullptr;       // small device scratch (null fit outputs)
@@ -289,13 +296,15 @@ bool streamed_feasible(Model& m) {
             cudaDeviceProp prop;
             ok = cudaGetDeviceProperties(&prop, m.device) == cudaSuccess;
             if (ok) {
-                // allocation granularity: 256 registers per warp, 1 KB of shared memory reserved per CTA
+                // Registers live in four per-scheduler files of regsPerMultiprocessor / 4 each; a CTA's warps are dealt
+                // round-robin to the schedulers and a warp is allocated in units of 256 registers.  Worst scheduler:
+                // 3 solve CTAs x 1 warp + 2 of the rotation CTA's 6 warps.  1 KB of shared memory is reserved per CTA.
                 auto warp_regs = [](int r) { return (r * 32 + 255) / 256 * 256; };
-                const int regs = 3 * 4 * warp_regs(s_regs) + 6 * warp_regs(r_regs);
+                const int per_sched = prop.regsPerMultiprocessor / 4;
+                const int regs = 3 * warp_regs(s_regs) + 2 * warp_regs(r_regs);
                 const size_t smem = 3 * (size_t)(s_smem + 1024) + (size_t)(r_smem + 1024);
                 // ... and a 4th solve CTA must not be able to take the rotation's slot
-                ok = regs <= prop.regsPerMultiprocessor && smem <= prop.sharedMemPerMultiprocessor &&
-                     4 * 4 * warp_regs(s_regs) > prop.regsPerMultiprocessor;
+                ok = regs <= per_sched && smem <= prop.sharedMemPerMultiprocessor && 4 * warp_regs(s_regs) > per_sched;
             }
         }
         cache[m.p] = ok ? 1 : -1;
@@ -433,7 +442,8 @@ int chunk_common(jxb_model* h, const float* host, size_t rows, bool rotated, con
 
 int scan_device_stages(jxb_model* h, const uint8_t* packed_dev, size_t bps, size_t rows, size_t n_full,
                        const int64_t* sidx_dev, size_t n_sel, bool have_mask, const jxb_qc_cfg* qc,
-                       const jxb_solve_cfg* cfg, int mode) {
+                       const jxb_solve_cfg* cfg, int mode, const float* prep_af_dev = nullptr,
+                       const uint8_t* prep_flip_dev = nullptr) {
     Model& m = h->m;
     h->last_nk = (size_t)-1;    // unknown on the host until the decode stage of the int8 path reads it back
     h->last_streamed = false;
@@ -446,6 +456,11 @@ int scan_device_stages(jxb_model* h, const uint8_t* packed_dev, size_t bps, size
     if (rc) return rc;
     if (have_mask) {
         apply_mask_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, m.stream>>>(m.counts, h->mask, (int)rows);
+        note_launch(1);
+    }
+    if (prep_af_dev || prep_flip_dev) {
+        apply_prepared_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, m.stream>>>(m.counts, m.af, prep_af_dev, prep_flip_dev,
+                                                                                  (int)rows);
         note_launch(1);
     }
     rc = launch_compact(m.counts, rows, m.src_row, m.n_kept, m.stream);
@@ -647,6 +662,9 @@ void jxb_model_destroy(jxb_model* h) {
         for (auto& e : h->ev) cudaEventDestroy(e);
     if (m.stream) cudaStreamDestroy(m.stream);
     if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
+    if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+    if (h->ev_copy) cudaEventDestroy(h->ev_copy);
+    if (h->packed2) cudaFree(h->packed2);
     if (h->ev_slab0) cudaEventDestroy(h->ev_slab0);
     if (h->ev_solve) cudaEventDestroy(h->ev_solve);
     for (void* t : {m.tmap_a8, m.tmap_q8_7, m.tmap_q8_3})
@@ -857,10 +875,10 @@ int jxb_scan_fetch_dev(jxb_model* h, size_t rows, int out_cols, double* out_dst_
     return 0;
 }
 
-int jxb_scan_packed(jxb_model* h, const uint8_t* packed, size_t bps, size_t rows, size_t n_full,
-                    const int64_t* sidx, const uint8_t* pre_keep, const jxb_qc_cfg* qc, const jxb_solve_cfg* cfg,
-                    int mode, uint8_t* keep_host, float* af_host, int32_t* missing_host, double* out_host,
-                    int32_t* evals_host, size_t* n_kept_host) {
+int jxb_scan_packed_prepared(jxb_model* h, const uint8_t* packed, size_t bps, size_t rows, size_t n_full,
+                             const int64_t* sidx, const uint8_t* pre_keep, const float* row_af, const uint8_t* row_flip,
+                             const jxb_qc_cfg* qc, const jxb_solve_cfg* cfg, int mode, uint8_t* keep_host, float* af_host,
+                             int32_t* missing_host, double* out_host, int32_t* evals_host, size_t* n_kept_host) {
     int rc = check_scan_args(h, bps, n_full, sidx, qc);
     if (rc) return rc;
     rc = check_cfg(cfg, mode);
@@ -879,10 +897,100 @@ int jxb_scan_packed(jxb_model* h, const uint8_t* packed, size_t bps, size_t rows
         sidx_dev = m.sample_idx;
     }
     if (pre_keep) JXB_CUDA_OK(cudaMemcpyAsync(h->mask, pre_keep, rows, cudaMemcpyHostToDevice, m.stream));
-    rc = scan_device_stages(h, m.packed, bps, rows, n_full, sidx_dev, m.n, pre_keep != nullptr, qc, cfg, mode);
+    if (row_af) JXB_CUDA_OK(cudaMemcpyAsync(h->prep_af, row_af, rows * sizeof(float), cudaMemcpyHostToDevice, m.stream));
+    if (row_flip) JXB_CUDA_OK(cudaMemcpyAsync(h->prep_flip, row_flip, rows, cudaMemcpyHostToDevice, m.stream));
+    rc = scan_device_stages(h, m.packed, bps, rows, n_full, sidx_dev, m.n, pre_keep != nullptr, qc, cfg, mode,
+                            row_af ? h->prep_af : nullptr, row_flip ? h->prep_flip : nullptr);
     if (rc) return rc;
     return jxb_scan_fetch(h, rows, h->last_out_cols, keep_host, af_host, missing_host, out_host, evals_host,
                           n_kept_host);
+}
+
+int jxb_stage_packed(jxb_model* h, const uint8_t* packed_host, size_t bps, size_t rows) {
+    if (!h || !packed_host) return fail(-2, "null argument");
+    if (rows == 0) return fail(-2, "cannot stage an empty batch");
+    Model& m = h->m;
+    if (h->staged) return fail(-2, "a staged batch is already waiting: run jxb_scan_staged_begin first");
+    if (h->cur_valid && (rows > m.cap_rows || bps > m.bps_cap))
+        return fail(-2, "cannot stage a batch larger than the workspace while another batch is current: stage the largest batch first");
+    int rc = ensure_capacity(h, rows, bps, false);
+    if (rc) return rc;
+    if (!h->copy_stream) {
+        JXB_CUDA_OK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        JXB_CUDA_OK(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
+    }
+    const size_t need = m.cap_rows * m.bps_cap;
+    if (h->packed2_bytes < need) {
+        if (h->packed2) cudaFree(h->packed2);
+        h->packed2 = nullptr;
+        h->packed2_bytes = 0;
+        JXB_CUDA_OK(cudaMalloc((void**)&h->packed2, need));
+        h->packed2_bytes = need;
+    }
+    JXB_CUDA_OK(cudaMemcpyAsync(h->packed2, packed_host, rows * bps, cudaMemcpyHostToDevice, h->copy_stream));
+    JXB_CUDA_OK(cudaEventRecord(h->ev_copy, h->copy_stream));
+    h->staged = true;
+    h->staged_rows = rows;
+    h->staged_bps = bps;
+    return 0;
+}
+
+int jxb_scan_staged_begin(jxb_model* h) {
+    if (!h) return fail(-2, "model is null");
+    if (!h->staged) return fail(-2, "no staged batch: call jxb_stage_packed first");
+    Model& m = h->m;
+    JXB_CUDA_OK(cudaSetDevice(m.device));
+    // the staged copy becomes the working buffer; the previous working buffer is the next staging target
+    JXB_CUDA_OK(cudaStreamWaitEvent(m.stream, h->ev_copy, 0));
+    std::swap(m.packed, h->packed2);
+    h->cur_rows = h->staged_rows;
+    h->cur_bps = h->staged_bps;
+    h->staged = false;
+    h->cur_valid = true;
+    return 0;
+}
+
+void jxb_stage_cancel(jxb_model* h) {
+    if (!h) return;
+    if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+    h->staged = false;
+    h->cur_valid = false;
+}
+
+int jxb_scan_staged(jxb_model* h, size_t n_full, const int64_t* sidx, const uint8_t* pre_keep, const float* row_af,
+                    const uint8_t* row_flip, const jxb_qc_cfg* qc, const jxb_solve_cfg* cfg, int mode, uint8_t* keep_host,
+                    float* af_host, int32_t* missing_host, double* out_host, int32_t* evals_host, size_t* n_kept_host) {
+    if (!h) return fail(-2, "model is null");
+    if (!h->cur_valid) return fail(-2, "no current batch: call jxb_stage_packed and jxb_scan_staged_begin first");
+    const size_t rows = h->cur_rows, bps = h->cur_bps;
+    h->cur_valid = false;
+    int rc = check_scan_args(h, bps, n_full, sidx, qc);
+    if (!rc) rc = check_cfg(cfg, mode);
+    if (rc) return rc;
+    Model& m = h->m;
+    if (rows > m.cap_rows || bps > m.bps_cap) return fail(-2, "internal error: staged batch exceeds the workspace");
+    tick(h, 0);
+    const int64_t* sidx_dev = nullptr;
+    if (sidx) {
+        rc = ensure_sample_idx(m, sidx, m.n, false, n_full);
+        if (rc) return rc;
+        sidx_dev = m.sample_idx;
+    }
+    if (pre_keep) JXB_CUDA_OK(cudaMemcpyAsync(h->mask, pre_keep, rows, cudaMemcpyHostToDevice, m.stream));
+    if (row_af) JXB_CUDA_OK(cudaMemcpyAsync(h->prep_af, row_af, rows * sizeof(float), cudaMemcpyHostToDevice, m.stream));
+    if (row_flip) JXB_CUDA_OK(cudaMemcpyAsync(h->prep_flip, row_flip, rows, cudaMemcpyHostToDevice, m.stream));
+    rc = scan_device_stages(h, m.packed, bps, rows, n_full, sidx_dev, m.n, pre_keep != nullptr, qc, cfg, mode,
+                            row_af ? h->prep_af : nullptr, row_flip ? h->prep_flip : nullptr);
+    if (rc) return rc;
+    return jxb_scan_fetch(h, rows, h->last_out_cols, keep_host, af_host, missing_host, out_host, evals_host, n_kept_host);
+}
+
+int jxb_scan_packed(jxb_model* h, const uint8_t* packed, size_t bps, size_t rows, size_t n_full,
+                    const int64_t* sidx, const uint8_t* pre_keep, const jxb_qc_cfg* qc, const jxb_solve_cfg* cfg,
+                    int mode, uint8_t* keep_host, float* af_host, int32_t* missing_host, double* out_host,
+                    int32_t* evals_host, size_t* n_kept_host) {
+    return jxb_scan_packed_prepared(h, packed, bps, rows, n_full, sidx, pre_keep, nullptr, nullptr, qc, cfg, mode, keep_host,
+                                    af_host, missing_host, out_host, evals_host, n_kept_host);
 }
 
 int jxb_decode_packed(jxb_model* h, const uint8_t* packed, size_t bps, size_t rows, size_t n_full,

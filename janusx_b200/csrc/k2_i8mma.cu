@@ -54,7 +54,7 @@ __device__ __forceinline__ void tile_coords(int tile, int mt_count, int nt_count
 // rows [row0, rows) of the operand planes are rotated (row0 is a multiple of the 256-row CTA tile); `corr` holds the
 // correction terms of these rows only, indexed r - row0.
 template <int NSL, int CG, bool SLIM>
-__global__ void __launch_bounds__(NTHREADS, SLIM ? 5 : 1)
+__global__ void __maxnreg__(SLIM ? 48 : 232)
 i8_rotate_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, int a_plane,
                  int slice0, int mode, int row0, int rows, int n, int kslabs, const double* __restrict__ coef,
                  const double* __restrict__ inv_scale, const double* __restrict__ rk, double* __restrict__ corr,

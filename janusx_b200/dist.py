@@ -40,8 +40,9 @@ def env_rank_world() -> Tuple[int, int, int]:
     return int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 
 
-def init_process_group(backend: Optional[str] = None):
-    """Rendezvous from RANK/WORLD_SIZE/MASTER_ADDR/MASTER_PORT (torchrun).  backend: nccl on GPUs, gloo on CPU."""
+def init_process_group(backend: Optional[str] = None, device_index: Optional[int] = None):
+    """Rendezvous from RANK/WORLD_SIZE/MASTER_ADDR/MASTER_PORT (torchrun).  backend: nccl on GPUs (one GPU per rank),
+    gloo on CPU or when ranks share a GPU.  device_index: this rank's CUDA device (default LOCAL_RANK)."""
     import torch
     import torch.distributed as dist
 
@@ -50,10 +51,13 @@ def init_process_group(backend: Optional[str] = None):
         return dist if dist.is_initialized() else None
     if backend is None:
         backend = "nccl" if torch.cuda.is_available() else "gloo"
+    dev = local if device_index is None else int(device_index)
     if backend == "nccl":
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+        torch.cuda.set_device(dev)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{dev}"))
     else:
+        if torch.cuda.is_available():
+            torch.cuda.set_device(dev)
         dist.init_process_group("gloo")
     return dist
 

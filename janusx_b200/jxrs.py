@@ -224,7 +224,7 @@ class DeviceModel:
                       genetic_model="add", want_g=True):
         packed = np.ascontiguousarray(packed, dtype=np.uint8)
         rows, bps = packed.shape
-        sidx = None if sample_idx is None else np.ascontiguousarray(sample_idx, dtype=np.int64)
+        sidx = self._sample_idx(sample_idx)
         qc = QcCfg(maf_thr, miss_thr, het_thr, _model_code(genetic_model))
         counts = np.zeros((rows, 4), dtype=np.int32)
         af = np.zeros(rows, dtype=np.float32)
@@ -235,15 +235,28 @@ class DeviceModel:
                                       ptr(counts), ptr(af), ptr(mr), ptr(g), C.byref(nk)))
         return counts, af, mr, (g[: nk.value] if want_g else None)
 
+    def _sample_idx(self, sample_idx):
+        if sample_idx is None:
+            return None
+        sidx = np.ascontiguousarray(sample_idx, dtype=np.int64).reshape(-1)
+        if sidx.shape[0] != self.n:      # the C ABI reads exactly n entries
+            raise RuntimeError(f"sample_indices length mismatch: got {sidx.shape[0]}, expected {self.n}")
+        return sidx
+
     def scan_packed(self, packed, n_full, sample_idx=None, pre_keep=None, maf_thr=0.02, miss_thr=0.05, het_thr=1.0,
                     genetic_model="add", mode="lmm", low=-5.0, high=5.0, max_iter=30, tol=1e-2, init=None,
-                    nullml=None, log10_lbd=None, return_evals=False):
-        """One batch of packed SNP rows -> (keep, af, missing, out[n_kept, cols])."""
+                    nullml=None, log10_lbd=None, return_evals=False, row_af=None, row_flip=None):
+        """One batch of packed SNP rows -> (keep, af, missing, out[n_kept, cols]).  row_af / row_flip: prepared row
+        metadata (the caller's imputation frequency and LUT flip per row, src/decode/decode.rs:163-219)."""
         packed = np.ascontiguousarray(packed, dtype=np.uint8) if isinstance(packed, np.ndarray) else packed
         rows, bps = int(packed.shape[0]), int(packed.shape[1])
         mode_i = {"lmm": 0, "lmm2": 1, "fvlmm": 2}[mode]
-        sidx = None if sample_idx is None else np.ascontiguousarray(sample_idx, dtype=np.int64)
+        sidx = self._sample_idx(sample_idx)
         pk = None if pre_keep is None else np.ascontiguousarray(pre_keep, dtype=np.uint8)
+        raf = None if row_af is None else np.ascontiguousarray(row_af, dtype=np.float32)
+        rfl = None if row_flip is None else np.ascontiguousarray(np.asarray(row_flip, dtype=bool), dtype=np.uint8)
+        if (raf is not None and raf.shape[0] != rows) or (rfl is not None and rfl.shape[0] != rows):
+            raise RuntimeError("row_flip/row_maf length mismatch with packed rows")
         qc = QcCfg(maf_thr, miss_thr, het_thr, _model_code(genetic_model))
         if mode_i == 2:
             init = log10_lbd
@@ -255,9 +268,9 @@ class DeviceModel:
         out = np.zeros((rows, cols), dtype=np.float64)
         ev = np.zeros(rows, dtype=np.int32)
         nk = C.c_size_t()
-        check(lib().jxb_scan_packed(self.handle, ptr(packed), bps, rows, int(n_full), ptr(sidx), ptr(pk), C.byref(qc),
-                                    C.byref(cfg), mode_i, ptr(keep), ptr(af), ptr(missing), ptr(out), ptr(ev),
-                                    C.byref(nk)))
+        check(lib().jxb_scan_packed_prepared(self.handle, ptr(packed), bps, rows, int(n_full), ptr(sidx), ptr(pk),
+                                             ptr(raf), ptr(rfl), C.byref(qc), C.byref(cfg), mode_i, ptr(keep), ptr(af),
+                                             ptr(missing), ptr(out), ptr(ev), C.byref(nk)))
         res = (keep.astype(bool), af, missing, out[: nk.value])
         return res + (ev[: nk.value],) if return_evals else res
 
@@ -305,7 +318,8 @@ class DeviceModel:
     def scan_bed_to_tsv(self, bed_prefix, out_tsv, maf_thr, miss_thr, het_thr, genetic_model="add", snps_only=False,
                         sample_ids=None, mode="lmm", low=-5.0, high=5.0, max_iter=30, tol=1e-2, nullml=None,
                         init=None, log10_lbd=None, batch_rows=4096, progress_callback=None, progress_every=0,
-                        snp_begin=0, snp_end=0, write_header=True, row_indices=None) -> int:
+                        snp_begin=0, snp_end=0, write_header=True, row_indices=None, row_maf=None, row_flip=None,
+                        row_missing=None, mmap_window_mb=None) -> int:
         cfg = BedScanCfg()
         cfg.bed_prefix = str(bed_prefix).encode()
         cfg.out_tsv = str(out_tsv).encode()
@@ -328,9 +342,19 @@ class DeviceModel:
         cfg.progress_every = int(progress_every)
         rows_keepalive = None
         if row_indices is not None:
-            rows_keepalive = np.ascontiguousarray(np.asarray(row_indices, dtype=np.int64))
-            cfg.row_indices = rows_keepalive.ctypes.data_as(C.POINTER(C.c_int64))
-            cfg.n_row_indices = rows_keepalive.shape[0]
+            rows_keepalive = [np.ascontiguousarray(np.asarray(row_indices, dtype=np.int64))]
+            cfg.row_indices = rows_keepalive[0].ctypes.data_as(C.POINTER(C.c_int64))
+            cfg.n_row_indices = rows_keepalive[0].shape[0]
+            for name, arr, ty, cty in (("row_maf", row_maf, np.float32, C.c_float), ("row_flip", row_flip, np.uint8, C.c_uint8),
+                                       ("row_missing", row_missing, np.float32, C.c_float)):
+                if arr is not None:
+                    a = np.ascontiguousarray(np.asarray(arr).astype(ty, copy=False).reshape(-1))
+                    if a.shape[0] != cfg.n_row_indices:
+                        raise RuntimeError(f"prepared row metadata length mismatch: row_indices={cfg.n_row_indices}, {name}={a.shape[0]}")
+                    rows_keepalive.append(a)
+                    setattr(cfg, name, a.ctypes.data_as(C.POINTER(cty)))
+        if mmap_window_mb:
+            cfg.mmap_window_mb = max(1, int(mmap_window_mb))
         err = []
 
         def _cb(done, total, _user):
@@ -528,9 +552,9 @@ def _check_bed_args(s, xcov, y_rot, u_t, low, high, tol):
 
 
 def _prepared_rows(row_indices, row_flip, row_missing, row_maf):
-    """Prepared row metadata (src/stats/lmm.rs:2576-2612): all four or none.  Only `row_indices` steers the device
-    scan (the listed rows are scanned without re-applying QC); allele frequency and missingness are recomputed from
-    the packed rows, which reproduces `row_maf` / `row_missing` whenever the metadata came from the same samples."""
+    """Prepared row metadata (src/stats/lmm.rs:2576-2612): all four or none.  The listed rows are scanned without
+    re-applying QC; `row_maf` is the imputation frequency (and the TSV af column), `row_flip` reverses the code LUT,
+    `row_missing` (a rate) becomes the TSV miss column through round(rate * n) -- all as the reference uses them."""
     given = [v is not None for v in (row_indices, row_flip, row_missing, row_maf)]
     if any(given) and not all(given):
         raise RuntimeError(
@@ -544,12 +568,11 @@ def _prepared_rows(row_indices, row_flip, row_missing, row_maf):
         raise RuntimeError(
             f"prepared row metadata length mismatch: row_indices={m}, row_flip={np.asarray(row_flip).shape[0]}, "
             f"row_maf={np.asarray(row_maf).shape[0]}, row_missing={np.asarray(row_missing).shape[0]}")
-    if np.any(np.asarray(row_flip, dtype=bool)):
-        raise NotImplementedError("row_flip=True is not supported (the reference never sets it on this path, "
-                                  "src/stats/lmm.rs:1316-1321)")
     if m > 1 and np.any(np.diff(idx) < 0):
         raise RuntimeError("prepared row_indices must be sorted in ascending BED order")
-    return idx
+    return dict(row_indices=idx, row_maf=np.asarray(row_maf, dtype=np.float32).reshape(-1),
+                row_flip=np.asarray(row_flip, dtype=bool).reshape(-1).astype(np.uint8),
+                row_missing=np.asarray(row_missing, dtype=np.float32).reshape(-1))
 
 
 def lmm_reml_assoc_bed_to_tsv_f32(bed_prefix, out_tsv, s, xcov, y_rot, u_t, maf_thr, miss_thr, het_thr,
@@ -557,14 +580,21 @@ def lmm_reml_assoc_bed_to_tsv_f32(bed_prefix, out_tsv, s, xcov, y_rot, u_t, maf_
                                   row_flip=None, row_missing=None, row_maf=None, low=-5.0, high=5.0, max_iter=30,
                                   tol=1e-2, threads=0, nullml=None, init_log10_lbd=None, rotate_block_rows=512,
                                   progress_callback=None, progress_every=0, mmap_window_mb=None) -> int:
-    """src/stats/lmm.rs:2488-2750.  Warm start is never used (JX_LMM_UNIFIED_NO_WARM_START=1 semantics:
-    every SNP starts from the interval midpoint), so `init_log10_lbd` only matters for LMM2."""
+    """src/stats/lmm.rs:2488-2750.  `init_log10_lbd` (clamped into [low, high], lmm.rs:2573-2575) seeds the Brent search
+    of EVERY SNP.  The reference additionally carries each rayon worker's last optimum to its next SNP
+    (use_warm_start, lmm.rs:134-161), which makes its rows depend on the thread schedule; that carry-over is never
+    used here (JX_LMM_UNIFIED_NO_WARM_START=1 semantics), so rows are independent of batch size and GPU count.  With
+    tol = 1e-2 a different Brent start moves lambda within the optimiser's tolerance: against a default-mode reference
+    run expect |d log10 lambda| <~ 1e-2 and beta/se agreement to ~1e-4 relative, not the 1e-8 of the no-warm-start mode."""
     _check_bed_args(s, xcov, y_rot, u_t, low, high, tol)
     _model_code(genetic_model)
     rows_sel = _prepared_rows(row_indices, row_flip, row_missing, row_maf)
     mdl = _get_model(s, xcov, y_rot, u_t)
+    init = None
+    if init_log10_lbd is not None and math.isfinite(init_log10_lbd):
+        init = min(max(float(init_log10_lbd), low), high)
     return mdl.scan_bed_to_tsv(bed_prefix, out_tsv, maf_thr, miss_thr, het_thr, genetic_model, snps_only, sample_ids,
-                               "lmm", low, high, max_iter, tol, nullml, None, None, row_indices=rows_sel,
+                               "lmm", low, high, max_iter, tol, nullml, init, None, mmap_window_mb=mmap_window_mb, **(rows_sel or {}),
                                batch_rows=max(int(rotate_block_rows), default_device_batch(mdl.n)), progress_callback=progress_callback,
                                progress_every=progress_every)
 
@@ -595,7 +625,7 @@ def lmm_reml_lmm2_assoc_bed_to_tsv_f32(bed_prefix, out_tsv, s, xcov, y_rot, u_t,
             raise RuntimeError("failed to optimize null ML for LMM2 unified scan")
     init = i_reml if i_reml is not None else i_ml
     return mdl.scan_bed_to_tsv(bed_prefix, out_tsv, maf_thr, miss_thr, het_thr, genetic_model, snps_only, sample_ids,
-                               "lmm2", low, high, max_iter, tol, nullml, init, None, row_indices=rows_sel,
+                               "lmm2", low, high, max_iter, tol, nullml, init, None, mmap_window_mb=mmap_window_mb, **(rows_sel or {}),
                                batch_rows=max(int(rotate_block_rows), default_device_batch(mdl.n)), progress_callback=progress_callback,
                                progress_every=progress_every)
 
@@ -613,7 +643,7 @@ def fvlmm_assoc_bed_to_tsv_f32(bed_prefix, out_tsv, s, xcov, y_rot, log10_lbd, u
     rows_sel = _prepared_rows(row_indices, row_flip, row_missing, row_maf)
     mdl = _get_model(s, xcov, y_rot, u_t)
     rows = mdl.scan_bed_to_tsv(bed_prefix, out_tsv, maf_thr, miss_thr, het_thr, genetic_model, snps_only, sample_ids,
-                               "fvlmm", nullml=nullml, log10_lbd=log10_lbd, row_indices=rows_sel,
+                               "fvlmm", nullml=nullml, log10_lbd=log10_lbd, mmap_window_mb=mmap_window_mb, **(rows_sel or {}),
                                batch_rows=max(int(rotate_block_rows), default_device_batch(mdl.n)), progress_callback=progress_callback,
                                progress_every=progress_every)
     # fvlmm.rs:2746-2753: pve = clamp(1 - ypy / sum y^2, 0, 1)
@@ -766,8 +796,6 @@ def _packed_args(packed, n_samples, row_flip, row_maf, s, xcov, y_rot, u_t, samp
     m = packed.shape[0]
     if np.asarray(row_flip).shape[0] != m or np.asarray(row_maf).shape[0] != m:
         raise RuntimeError("row_flip/row_maf length mismatch with packed rows")
-    if np.any(np.asarray(row_flip, dtype=bool)):
-        raise NotImplementedError("row_flip=True is not supported (never set by the reference on this path)")
     n = np.asarray(y_rot).reshape(-1).shape[0]
     if n == 0:
         raise RuntimeError("y_rot must not be empty")
@@ -784,32 +812,29 @@ def _packed_args(packed, n_samples, row_flip, row_maf, s, xcov, y_rot, u_t, samp
     return np.ascontiguousarray(packed, dtype=np.uint8), sidx
 
 
-def _scan_packed_all_rows(mdl, packed, n_samples, sidx, row_maf, model, low, high, max_iter, tol, init, nullml,
+def _scan_packed_all_rows(mdl, packed, n_samples, sidx, row_maf, row_flip, model, low, high, max_iter, tol, init, nullml,
                           progress_callback, progress_every):
-    """Every supplied row is scanned (thresholds off: the caller already filtered).  The device recomputes the
-    allele frequency that drives imputation; a `row_maf` that disagrees means the metadata belongs to other
-    samples, which is refused rather than silently ignored."""
+    """Every supplied row is scanned (thresholds off: the caller already filtered).  `row_maf` is the imputation
+    frequency exactly as the reference uses it (mean_g = 2 * row_maf, src/decode/decode.rs:213-219) -- it need not be
+    the frequency over the selected samples (workflow_model_packed.py:1296 passes full-sample values) -- and `row_flip`
+    reverses the code LUT."""
     m = packed.shape[0]
     cols = 4 if nullml is not None else 3
     out = np.zeros((m, cols), dtype=np.float64)
-    af_all = np.zeros(m, dtype=np.float32)
     miss_all = np.zeros(m, dtype=np.int32)
+    raf = np.ascontiguousarray(np.asarray(row_maf, dtype=np.float32).reshape(-1))
+    rfl = np.ascontiguousarray(np.asarray(row_flip, dtype=bool).reshape(-1))
     step = default_device_batch(mdl.n) if not progress_every else max(1, min(int(progress_every), default_device_batch(mdl.n)))
     for r0 in range(0, m, step):
         r1 = min(m, r0 + step)
         keep, af, missing, res = mdl.scan_packed(packed[r0:r1], n_samples, sidx, None, 0.0, 1.0, 0.0, model, "lmm", low, high,
-                                                 max_iter, tol, init, nullml)
+                                                 max_iter, tol, init, nullml, row_af=raf[r0:r1],
+                                                 row_flip=(rfl[r0:r1] if rfl.any() else None))
         if not keep.all():
             raise RuntimeError("internal error: packed scan dropped rows with QC disabled")
-        out[r0:r1], af_all[r0:r1], miss_all[r0:r1] = res, af, missing
+        out[r0:r1], miss_all[r0:r1] = res, missing
         if progress_callback is not None:
             progress_callback(r1, m)
-    want = np.asarray(row_maf, dtype=np.float32)
-    bad = ~((want == af_all) | (np.isnan(want) & np.isnan(af_all)))
-    if bad.any():
-        i = int(np.nonzero(bad)[0][0])
-        raise RuntimeError(f"row_maf[{i}]={want[i]!r} differs from the allele frequency of the packed row over the "
-                           f"selected samples ({af_all[i]!r}); prepared metadata must come from the same samples")
     return out, miss_all
 
 
@@ -825,8 +850,8 @@ def lmm_reml_assoc_packed_f32(packed, n_samples, row_flip, row_maf, s, xcov, y_r
     if init_log10_lbd is not None and math.isfinite(init_log10_lbd):
         init = min(max(float(init_log10_lbd), low), high)
     mdl = _get_model(s, xcov, y_rot, u_t)
-    out, _ = _scan_packed_all_rows(mdl, packed, n_samples, sidx, row_maf, model, low, high, max_iter, tol, init, nullml,
-                                   progress_callback, progress_every)
+    out, _ = _scan_packed_all_rows(mdl, packed, n_samples, sidx, row_maf, row_flip, model, low, high, max_iter, tol, init,
+                                   nullml, progress_callback, progress_every)
     return out
 
 
@@ -876,8 +901,8 @@ def lmm_reml_assoc_packed_f32_to_tsv(packed, n_samples, row_flip, row_maf, row_m
     if init_log10_lbd is not None and math.isfinite(init_log10_lbd):
         init = min(max(float(init_log10_lbd), low), high)
     mdl = _get_model(s, xcov, y_rot, u_t)
-    out, _ = _scan_packed_all_rows(mdl, packed, n_samples, sidx, row_maf, model, low, high, max_iter, tol, init, nullml,
-                                   progress_callback, progress_every)
+    out, _ = _scan_packed_all_rows(mdl, packed, n_samples, sidx, row_maf, row_flip, model, low, high, max_iter, tol, init,
+                                   nullml, progress_callback, progress_every)
     n = mdl.n
     rate = np.asarray(row_missing, dtype=np.float32)
     cnt = np.where(np.isfinite(rate) & (rate > 0), np.round(rate.astype(np.float64) * n), 0.0)

@@ -2,7 +2,8 @@
 
 Reads   /root/reference/example/mouse_hs1940.vcf.gz  (1,940 heterogeneous-stock mice, 10,300 sites, GT only)
         /root/reference/example/mouse_hs1940.pheno    (6 traits, NA = missing)
-Writes  tests/golden/mouse_hs1940_sub.vcf.gz          (header + the first 1,500 records, bytes unchanged)
+Writes  tests/golden/mouse_hs1940_full.vcf.gz         (all 10,300 records: the input of configs[0] as BASELINE.json names it)
+        tests/golden/mouse_hs1940_sub.vcf.gz          (header + the first 1,500 records, bytes unchanged; fast CLI test)
         tests/golden/mouse_hs1940_sub.pheno           (sample id + traits test0, test3)
 The reference holds no expected association output for this data set, so the fixture supplies real
 genotype structure (relatedness, real allele-frequency spectrum) as INPUT; expectations come from the oracle at test
@@ -19,6 +20,8 @@ N_RECORDS = 1500
 
 
 def main():
+    import shutil
+    shutil.copyfile(SRC / "mouse_hs1940.vcf.gz", OUT / "mouse_hs1940_full.vcf.gz")
     kept, records = [], 0
     with gzip.open(SRC / "mouse_hs1940.vcf.gz", "rt") as fh:
         for line in fh:

@@ -227,8 +227,6 @@ def test_packed_entry_point_validation_and_writer_text_paths(tmp_path):
                     (dict(u_t=np.eye(n - 1, dtype=np.float32)), "u_t must be"), (dict(model="mult"), "model must be one of")):
         with pytest.raises((RuntimeError, ValueError), match=msg):
             call(**kw)
-    with pytest.raises(NotImplementedError):
-        call(row_flip=np.ones(m, bool))
     w = jxrs.GwasAssocTsvWriter(str(tmp_path / "t.tsv"))
     w.append_text("", True, 0)                                  # no-op: nothing opened yet
     with pytest.raises(IOError):

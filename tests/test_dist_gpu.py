@@ -67,3 +67,49 @@ def test_two_rank_device_scan_equals_single(tmp_path, oracle):
     assert all(p.returncode == 0 for p in procs), "\n".join(outs)
     assert f"TOTAL {rows1}" in outs[0]
     assert (tmp_path / "sharded.tsv").read_bytes() == single.read_bytes()
+
+
+def _run_cli(args, timeout=900):
+    env = dict(os.environ, PYTHONPATH=str(ROOT) + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    r = subprocess.run([sys.executable, "-m", "janusx_b200.gwas", *args], env=env, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True, timeout=timeout)
+    assert r.returncode == 0, r.stdout
+    return r.stdout
+
+
+def test_cli_one_job_on_n_ranks_is_byte_identical(tmp_path, oracle):
+    """The shipped multi-GPU job (`python -m janusx_b200.gwas ... -gpus N`, src/stats/lmm.rs:2488-2750 scans the whole BED
+    in one call): rank 0 GRM + eigh + null fit -> one broadcast -> contiguous SNP shards -> ordered concatenation.
+    The TSV must be byte-identical for N = 1, 2, 3 (ranks take distinct GPUs when the box has them and rendezvous over
+    NCCL; on a 1-GPU box they share cuda:0 over gloo), and sampled rows match the oracle on the N-rank output."""
+    import torch
+    sys.path.insert(0, str(ROOT / "tests"))
+    from conftest import make_problem
+    from janusx_b200 import synth
+    from test_parity_gpu import _assert_row_equiv, _tsv_fields
+    case = make_problem(n=400, m=3000, q=0, seed=123, missing_rate=0.02)
+    prefix = str(tmp_path / "panel")
+    synth.write_plink(prefix, case.packed, case.n)
+    with open(tmp_path / "pheno.tsv", "w") as fh:
+        fh.write("id\ttraitA\n")
+        for j in range(case.n):
+            fh.write(f"S{j}\t{case.y[j]:.10f}\n")
+    outs = {}
+    ndev = torch.cuda.device_count()
+    counts = [1, 2, 3] if ndev < 4 else [1, 2, 4, min(8, ndev)]
+    for g in counts:
+        out = tmp_path / f"out{g}"
+        log = _run_cli(["-bfile", prefix, "-p", str(tmp_path / "pheno.tsv"), "-lmm", "-lmm2", "-fvlmm", "-k", "1", "-q", "2",
+                        "-force-model", "-gpus", str(g), "-o", str(out), "-prefix", "run"])
+        outs[g] = {m: (out / f"run.traitA.{m}.tsv").read_bytes() for m in ("lmm", "lmm2", "fvlmm")}
+        assert not list(out.glob("*.part*")) and not list(out.glob("*.tmp")), log
+    for g in counts[1:]:
+        for m in ("lmm", "lmm2", "fvlmm"):
+            assert outs[g][m] == outs[1][m], (g, m)
+    # every kept SNP exactly once, in BED order
+    keep, af, mr, missing = oracle.count_qc_block(case.packed, case.n, None, 0.02, 0.05, 1.0)
+    lines = outs[counts[-1]]["lmm"].split(b"\n")
+    assert len(lines) == int(keep.sum()) + 2
+    assert [l.split(b"\t")[2] for l in lines[1:-1]] == [f"snp{i}".encode() for i in np.nonzero(keep)[0]]

@@ -345,18 +345,37 @@ def _tsv_fields(path):
     return lines[0], [l.split(b"\t") for l in lines[1:-1]]
 
 
+def _last_digit_unit(text):
+    """Value of one unit in the last printed digit of a TSV number (`{:.4}` / `{:.4e}` / `{:.6e}` renderings)."""
+    text = text.decode() if isinstance(text, bytes) else text
+    if "e" in text:
+        mant, ex = text.split("e")
+        digits = len(mant.split(".")[1]) if "." in mant else 0
+        return 10.0 ** (int(ex) - digits)
+    return 10.0 ** (-(len(text.split(".")[1]) if "." in text else 0))
+
+
+def _assert_row_equiv(a, b):
+    """Two TSV rows of the same SNP: identification columns byte-exact; a numeric field may differ only by ONE unit of
+    its last printed digit (two doubles within the 1e-8 gate on either side of a rounding boundary)."""
+    assert a[:7] == b[:7]          # chrom pos snp alleles af miss: byte-exact
+    for x, y in zip(a[7:], b[7:]):
+        if x == y:
+            continue
+        fx, fy = float(x), float(y)
+        assert not (math.isnan(fx) or math.isnan(fy)), (x, y)
+        assert abs(fx - fy) <= 1.0001 * max(_last_digit_unit(x), _last_digit_unit(y)), (x, y)
+
+
 def _assert_tsv_equiv(got_path, want_path):
     hg, rg = _tsv_fields(got_path)
     hw, rw = _tsv_fields(want_path)
     assert hg == hw and len(rg) == len(rw)
     mismatched = 0
     for a, b in zip(rg, rw):
-        assert a[:7] == b[:7]          # chrom pos snp alleles af miss: byte-exact
-        if a[7:] != b[7:]:
+        if a != b:
             mismatched += 1
-            for x, y in zip(a[7:], b[7:]):   # a 4-decimal rounding boundary may flip the last digit
-                fx, fy = float(x), float(y)
-                assert (math.isnan(fx) and math.isnan(fy)) or math.isclose(fx, fy, rel_tol=2e-4, abs_tol=1.01e-4)
+            _assert_row_equiv(a, b)
     assert mismatched <= max(1, len(rw) // 200)
 
 
@@ -584,11 +603,59 @@ def test_full_size_n20000_parity_sample(jx, oracle):
         np.testing.assert_allclose(out[:, 4], want[:, 4], rtol=1e-10)
 
 
-def test_full_batch_at_full_size_sampled_parity(jx, oracle):
-    """One full device batch (75,776 SNP rows = the bench step) at n = 20,000 (JXB_TEST_FULL_N=50000 for BASELINE
-    configs[3]): rows sampled from the start, middle and end of the batch are checked against the oracle, which
-    catches 32-bit index overflow in any kernel (rows x n exceeds 2^31 at n = 50,000)."""
-    import os
+def test_prepared_row_maf_and_flip_are_used_as_given(jx, oracle, tmp_path):
+    """Prepared row metadata as the reference consumes it (src/decode/decode.rs:163-219, src/stats/lmm.rs:1237-1262):
+    `row_maf` is the imputation frequency even when it is NOT the frequency over the scanned samples
+    (workflow_model_packed.py:1296 passes full-sample values), `row_flip` reverses the code LUT, and the BED entry point
+    prints `row_maf` / round(row_missing * n) / n in the af / miss columns."""
+    from janusx_b200 import synth
+    case = make_problem(n=320, m=240, q=2, seed=91, missing_rate=0.04)
+    nm = null_model(oracle, case)
+    n, m = case.n, 240
+    rng = np.random.default_rng(5)
+    _, af, mr, _ = oracle.count_qc_block(case.packed, n, None, 0.0, 1.0, 0.0)
+    flip = rng.random(m) < 0.3
+    row_maf = np.where(flip, 1.0 - af, af).astype(np.float32)
+    row_maf[::5] = np.float32(0.37)                                  # deliberately not the sample frequency
+    g = oracle.decode_centered_block(case.packed, n, row_maf, flip=flip)
+    want = oracle.lmm_reml_chunk_f32(case.s, nm["xcov"], nm["y"], nm["low"], nm["high"], oracle.rotate_block(g, nm["ut"]), 50, 1e-2)
+    got = jx.lmm_reml_assoc_packed_f32(case.packed, n, flip, row_maf, case.s, nm["xcov"], nm["y"], nm["ut"], low=nm["low"],
+                                       high=nm["high"])
+    assert_results_close(got, want)
+    # non-additive coding takes the FP64 decode path: same override
+    g_d = oracle.decode_centered_block(case.packed, n, row_maf, flip=flip, model="dom")
+    want_d = oracle.lmm_reml_chunk_f32(case.s, nm["xcov"], nm["y"], nm["low"], nm["high"], oracle.rotate_block(g_d, nm["ut"]), 50, 1e-2)
+    got_d = jx.lmm_reml_assoc_packed_f32(case.packed, n, flip, row_maf, case.s, nm["xcov"], nm["y"], nm["ut"], low=nm["low"],
+                                         high=nm["high"], model="dom")
+    assert_results_close(got_d, want_d)
+    # BED entry point with the four prepared arrays
+    prefix = str(tmp_path / "prep")
+    synth.write_plink(prefix, case.packed, n)
+    listed = np.arange(3, m, 2)
+    miss_rate = mr[listed].copy()
+    miss_rate[0] = np.float32(0.0301)                                # round(0.0301 * 320) = 10 -> 10 / 320
+    rows = jx.lmm_reml_assoc_bed_to_tsv_f32(prefix, str(tmp_path / "p.tsv"), case.s, nm["xcov"], nm["y"], nm["ut"], 0.02, 0.05,
+                                            1.0, low=nm["low"], high=nm["high"], max_iter=50, row_indices=listed,
+                                            row_flip=flip[listed], row_missing=miss_rate, row_maf=row_maf[listed])
+    assert rows == listed.size
+    head, body = _tsv_fields(tmp_path / "p.tsv")
+    bim = oracle.read_bim(prefix)
+    for k, j in enumerate(listed):
+        chrom, snp_id, pos, a0, a1 = bim[j]
+        cnt = 0.0 if not (np.isfinite(miss_rate[k]) and miss_rate[k] > 0) else np.round(float(miss_rate[k]) * n)
+        rate = float(np.float32(cnt) / np.float32(n))
+        line = oracle.format_row(chrom, pos, snp_id, a0, a1, float(row_maf[j]), rate, want[j]).rstrip(b"\n").split(b"\t")
+        _assert_row_equiv(body[k], line)
+    assert body[0][6] == b"0.0312"
+
+
+@pytest.mark.parametrize("n,model", [(20000, "lmm2"), (50000, "lmm")])
+def test_full_batch_at_full_size_sampled_parity(jx, oracle, n, model):
+    """One full device batch (75,776 SNP rows) at the sample counts of BASELINE.json configs[2] / [4] (n = 20,000: -lmm2,
+    then -fvlmm on the same batch) and configs[3] (n = 50,000, -lmm): rows sampled from the start, middle and end of the
+    batch are checked against the oracle, which catches 32-bit index overflow in any kernel (rows x n exceeds 2^31 at
+    n = 50,000).  The n = 20,000 batch runs the streamed scan (rotation slabs under the persistent solve kernel) and
+    is repeated with the overlap switched off: bit-identical."""
     import sys
     from pathlib import Path
     import torch
@@ -596,21 +663,10 @@ def test_full_batch_at_full_size_sampled_parity(jx, oracle):
     if root not in sys.path:
         sys.path.insert(0, root)
     import bench as B
-    n = int(os.environ.get("JXB_TEST_FULL_N", 20000))
     rows, q = 75776, 3
     dev = torch.device("cuda:0")
-    if n <= 46340:
-        s_np, u_t_dev, X_np, y_np = B.build_null_model(torch, n, 4096, q, dev)
-    else:
-        # cuSOLVER's Xsyevd rejects n*n >= 2^31: two unrelated half-size populations = block-diagonal GRM / U^T
-        h = n // 2
-        s1, u1, X1, y1 = B.build_null_model(torch, h, 4096, q, dev)
-        s2, u2, X2, y2 = B.build_null_model(torch, n - h, 2048, q, dev)
-        u_t_dev = torch.zeros((n, n), dtype=torch.float32, device=dev)
-        u_t_dev[:h, :h] = u1
-        u_t_dev[h:, h:] = u2
-        del u1, u2
-        s_np, X_np, y_np = np.concatenate([s1, s2]), np.concatenate([X1, X2]), np.concatenate([y1, y2])
+    # n > 46,340: two unrelated half-size populations = block-diagonal GRM / U^T (bench.build_null_model)
+    s_np, u_t_dev, X_np, y_np = B.build_null_model(torch, n, 4096, q, dev)
     ut = u_t_dev.cpu().numpy()
     mdl = jx.DeviceModel(s_np, np.ones((n, q + 1)), np.zeros(n), u_t_dev, device=0, u_t_on_device=True)
     del u_t_dev
@@ -620,12 +676,17 @@ def test_full_batch_at_full_size_sampled_parity(jx, oracle):
     lbd_o, _, _ = oracle.lmm_reml_null_f32(s_np, xo, yo[:, 0], -5.0, 5.0, 50, 1e-3)
     l10 = float(np.log10(lbd_o))
     lo, hi = l10 - 2.0, l10 + 2.0
-    _, nullml = oracle.lmm_ml_null_brent(s_np, xo, yo[:, 0], lo, hi, 30, 1e-2, l10)
+    nullml = None
+    if model == "lmm2":
+        _, nullml = oracle.lmm_ml_null_brent(s_np, xo, yo[:, 0], lo, hi, 30, 1e-2, l10)
     pk, _ = B.gen_packed_batch(torch, n, rows, 4242, dev)
+    pk[3, :50] = 0b01010101            # missing calls in one row: the whole batch takes the missing-indicator pass
     bps = pk.shape[1]
     torch.cuda.synchronize(dev)          # the scan runs on the model's own stream
-    cols = mdl.scan_packed_dev(pk.data_ptr(), rows, bps, n, None, mode="lmm2", low=lo, high=hi, init=l10, nullml=nullml)
+    kw = dict(mode=model, low=lo, high=hi, init=(l10 if model == "lmm2" else None), nullml=nullml)
+    cols = mdl.scan_packed_dev(pk.data_ptr(), rows, bps, n, None, **kw)
     keep, af, missing, out, ev = mdl.scan_fetch(rows, cols)
+    streamed = mdl.stage_ms()["streamed"] > 0
     assert keep.sum() == out.shape[0], (int(keep.sum()), out.shape)
     assert keep.sum() > rows * 0.99, int(keep.sum())
     pos = np.cumsum(keep) - 1                                   # source row -> compacted row
@@ -635,11 +696,90 @@ def test_full_batch_at_full_size_sampled_parity(jx, oracle):
     assert keep_o.all() and np.array_equal(af_o.view(np.uint32), af[picks].view(np.uint32))
     assert np.array_equal(miss_o, missing[picks])
     g = oracle.decode_centered_block(sub, n, af_o)
-    want = oracle.lmm_reml_lmm2_chunk_f32(s_np, xo, yo[:, 0], lo, hi, oracle.rotate_block(g, ut), nullml, 30, 1e-2,
-                                          init_reml=l10)
+    rot_o = oracle.rotate_block(g, ut)
     got = out[pos[picks]]
-    assert_results_close(got, want, cols_p=(2, 5), cols_lambda=(3,))
-    np.testing.assert_allclose(got[:, 4], want[:, 4], rtol=1e-10)
+    if model == "lmm2":
+        want, ev_o = oracle.lmm_reml_lmm2_chunk_f32(s_np, xo, yo[:, 0], lo, hi, rot_o, nullml, 30, 1e-2, init_reml=l10), None
+        assert_results_close(got, want, cols_p=(2, 5), cols_lambda=(3,))
+        np.testing.assert_allclose(got[:, 4], want[:, 4], rtol=1e-10)
+    else:
+        want, ev_o = oracle.lmm_reml_chunk_f32(s_np, xo, yo[:, 0], lo, hi, rot_o, 30, 1e-2, return_evals=True)
+        assert_results_close(got, want)
+        assert np.array_equal(ev[pos[picks]], ev_o)             # the same Brent path, evaluation for evaluation
+    if n <= 24000:
+        assert streamed, "the n = 20,000 batch should take the streamed (overlapped) scan"
+        # rotate-then-solve on the same batch: same kernels' arithmetic, bit-identical rows
+        jx.set_stream_overlap(False)
+        try:
+            mdl.scan_packed_dev(pk.data_ptr(), rows, bps, n, None, **kw)
+            keep2, af2, missing2, out2, ev2 = mdl.scan_fetch(rows, cols)
+            assert mdl.stage_ms()["streamed"] == 0
+        finally:
+            jx.set_stream_overlap(True)
+        assert np.array_equal(keep, keep2) and np.array_equal(out, out2, equal_nan=True) and np.array_equal(ev, ev2)
+        # BASELINE.json configs[4]: -fvlmm (fixed lambda = null lambda) on the same full batch
+        cols_f = mdl.scan_packed_dev(pk.data_ptr(), rows, bps, n, None, mode="fvlmm", log10_lbd=l10)
+        keep_f, _, _, out_f, _ = mdl.scan_fetch(rows, cols_f)
+        assert np.array_equal(keep_f, keep) and out_f.shape == (int(keep.sum()), 3)
+        want_f, _ = oracle.lmm_assoc_chunk_f32(s_np, xo, yo[:, 0], l10, rot_o, 0, None)
+        assert_results_close(out_f[pos[picks]], want_f)
+        assert np.isfinite(out_f[:, :2]).all()
+
+
+def test_config2_bed_to_tsv_n5000(jx, oracle, tmp_path):
+    """BASELINE.json configs[1] shape: n = 5,000, 3 covariates, -lmm through the file-level entry point
+    (jxb_scan_bed_to_tsv) on a 131,072-SNP PLINK file.  Every row's identification / af / miss columns are checked
+    against the oracle's counts; 18 sampled rows are checked as text and as numbers at the north-star gates."""
+    import sys
+    from pathlib import Path
+    import torch
+    from janusx_b200 import synth
+    root = str(Path(__file__).resolve().parents[1])
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    import bench as B
+    n, m, q = 5000, 131072, 3
+    dev = torch.device("cuda:0")
+    s_np, u_t_dev, X_np, y_np = B.build_null_model(torch, n, 4096, q, dev)
+    ut = u_t_dev.cpu().numpy()
+    del u_t_dev
+    xo, yo = oracle.lmm_rotate_x_y_with_ut_f64(ut, X_np, y_np)
+    lbd_o, _, _ = oracle.lmm_reml_null_f32(s_np, xo, yo[:, 0], -5.0, 5.0, 50, 1e-3)
+    l10 = float(np.log10(lbd_o))
+    lo, hi = l10 - 2.0, l10 + 2.0
+    packed = B.gen_snp_range(torch, n, 0, m, dev).cpu().numpy()
+    packed[17, :30] = 0b01010101          # a row with missing calls
+    prefix = str(tmp_path / "c2")
+    synth.write_plink(prefix, packed, n)
+    out_tsv = tmp_path / "c2.lmm.tsv"
+    rows = jx.lmm_reml_assoc_bed_to_tsv_f32(prefix, str(out_tsv), s_np, xo, yo[:, 0], ut, 0.02, 0.05, 1.0, low=lo, high=hi)
+    keep, af, mr, missing = oracle.count_qc_block(packed, n, None, 0.02, 0.05, 1.0)
+    idx = np.nonzero(keep)[0]
+    assert rows == idx.size > 0.95 * m
+    head, body = _tsv_fields(out_tsv)
+    assert len(head.split(b"\t")) == 11 and len(body) == rows
+    bim = oracle.read_bim(prefix)
+    for k in range(0, rows, 97):                      # SNP order, af and miss columns over the whole file
+        j = idx[k]
+        chrom, snp_id, pos, a0, a1 = bim[j]
+        name = snp_id if snp_id not in ("", ".") else f"{chrom}_{pos}"
+        rate = np.float32(missing[j]) / np.float32(n)
+        assert body[k][:7] == [v.encode() for v in (chrom, str(pos), name, a0, a1, "%.4f" % float(af[j]), "%.4f" % float(rate))], k
+    picks = np.concatenate([np.arange(0, 6), np.arange(rows // 2, rows // 2 + 6), np.arange(rows - 6, rows)])
+    src = idx[picks]
+    g = oracle.decode_centered_block(packed, n, af[src], row_indices=src)
+    want = oracle.lmm_reml_chunk_f32(s_np, xo, yo[:, 0], lo, hi, oracle.rotate_block(g, ut), 30, 1e-2)
+    for k, j, w in zip(picks, src, want):
+        chrom, snp_id, pos, a0, a1 = bim[j]
+        rate = float(np.float32(missing[j]) / np.float32(n))
+        line = oracle.format_row(chrom, pos, snp_id, a0, a1, float(af[j]), rate, w).rstrip(b"\n").split(b"\t")
+        _assert_row_equiv(body[k], line)
+    # the same rows as numbers, through the packed entry point of the same model
+    mdl = jx._get_model(s_np, xo, yo[:, 0], ut)
+    k_d, af_d, miss_d, out_d = mdl.scan_packed(np.ascontiguousarray(packed[src]), n, low=lo, high=hi, maf_thr=0.0, miss_thr=1.0,
+                                               het_thr=0.0)
+    assert k_d.all() and np.array_equal(af_d.view(np.uint32), af[src].view(np.uint32)) and np.array_equal(miss_d, missing[src])
+    assert_results_close(out_d, want)
 
 
 def test_cli_gwas_lmm_end_to_end(jx, oracle, tmp_path):
@@ -654,7 +794,7 @@ def test_cli_gwas_lmm_end_to_end(jx, oracle, tmp_path):
         for j in range(case.n):
             fh.write(f"S{j}\t{case.y[j]:.10f}\n" if j != 7 else f"S{j}\tNA\n")   # one missing phenotype
     rc = gwas.main(["-bfile", prefix, "-p", str(tmp_path / "pheno.tsv"), "-n", "0", "-lmm", "-lmm2", "-fvlmm",
-                    "-k", "1", "-o", str(tmp_path / "out"), "-prefix", "run"])
+                    "-k", "1", "-mem", "64MB", "-o", str(tmp_path / "out"), "-prefix", "run"])
     assert rc == 0
     for model, ncols in (("lmm", 11), ("lmm2", 14), ("fvlmm", 11)):
         lines = (tmp_path / "out" / f"run.traitA.{model}.tsv").read_text().splitlines()
@@ -662,3 +802,24 @@ def test_cli_gwas_lmm_end_to_end(jx, oracle, tmp_path):
         assert len(lines[0].split("\t")) == ncols and len(lines) > 100
         assert all(len(l.split("\t")) == ncols for l in lines[1:])
     assert not list((tmp_path / "out").glob("*.tmp"))
+
+
+def test_cli_lm_switch_without_force_model(jx, tmp_path, capsys):
+    """workflow_model_stream.py:930-963: a trait whose null LRT of Va = 0 is not significant is switched to LM by the
+    reference.  LM is outside this build, so the trait is skipped with the reference's warning (exit code 3) unless
+    -force-model keeps the mixed model."""
+    from janusx_b200 import gwas, synth
+    case = make_problem(n=240, m=400, q=0, seed=5, missing_rate=0.0)
+    prefix = str(tmp_path / "panel")
+    synth.write_plink(prefix, case.packed, case.n)
+    rng = np.random.default_rng(1)
+    with open(tmp_path / "pheno.tsv", "w") as fh:
+        fh.write("id\tnoise\n")
+        for j in range(case.n):
+            fh.write(f"S{j}\t{rng.normal():.10f}\n")      # no genetic component at all
+    common = ["-bfile", prefix, "-p", str(tmp_path / "pheno.tsv"), "-lmm", "-k", "1", "-o", str(tmp_path / "out"), "-prefix", "r"]
+    rc = gwas.main(common)
+    err = capsys.readouterr().err
+    assert rc == 3 and "switch to LM for trait noise" in err and not (tmp_path / "out" / "r.noise.lmm.tsv").exists()
+    rc = gwas.main(common + ["-force-model"])
+    assert rc == 0 and (tmp_path / "out" / "r.noise.lmm.tsv").exists()
