@@ -65,8 +65,9 @@ def parse_args():
     ap.add_argument("--rotate-variant", type=int, default=int(os.environ.get("JXB_BENCH_ROTATE", 3)),
                     help="3 = hand-written tcgen05 int8-sliced exact rotation (default), 2 = same via cuBLASLt, "
                          "0 = FP64 DMMA GEMM")
-    ap.add_argument("--overlap", type=int, default=int(os.environ.get("JXB_BENCH_OVERLAP", 1)),
-                    help="1 = streamed scan: rotation slabs under one persistent solve kernel (default)")
+    ap.add_argument("--overlap", type=int, default=int(os.environ.get("JXB_BENCH_OVERLAP", 0)),
+                    help="1 = streamed scan: rotation slabs under one persistent solve kernel (measured slower: both kernels "
+                         "are bound by the shared-memory pipe); 0 = rotate then solve (default)")
     ap.add_argument("--slab", type=int, default=int(os.environ.get("JXB_BENCH_SLAB", 0)), help="rows per rotation slab")
     return ap.parse_args()
 

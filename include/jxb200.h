@@ -195,6 +195,13 @@ void jxb_set_thread_solve_min_rows(size_t rows);
 /* Kernel for those large batches: 0 (default) = lane-per-SNP with refill on the row-major block, 1 = the earlier
  * thread-per-SNP kernel on an SNP-minor block (tcgen05 rotation only).  Same per-SNP arithmetic, identical results. */
 void jxb_set_big_solve_kernel(int variant);
+/* The large-batch solve kernels take their per-sample 1/(s_i + lambda) from a branch-free copy of the compiler's own f64
+ * reciprocal sequence whenever every s_i + lambda of the search interval lies in [1e-290, 1e290] (bit-identical
+ * results; no divide slow path in the sample loops).  jxb_set_generic_divide(1) forces the compiler-generated divide
+ * (tests compare the two); jxb_selftest_rcp compares `count` pseudo-random values with binary exponents in
+ * [lo_exp, hi_exp] (extreme mantissas included) and returns the number of differing bit patterns. */
+void jxb_set_generic_divide(int on);
+int jxb_selftest_rcp(size_t count, int lo_exp, int hi_exp, uint64_t* mismatches);
 /* Streamed scan (default on): large additive LMM / LMM2 batches are rotated in slabs of `slab_rows` rows (0 = keep the
  * current value, default 8192) while ONE persistent solve kernel consumes the rows already rotated -- the tensor pipe
  * (rotation) and the FP64 pipe (solve) of every SM work at the same time.  Same kernels' arithmetic, identical results.
@@ -297,6 +304,10 @@ int jxb_vcf_to_plink(const char* vcf_path, const char* out_prefix, int snps_only
  *     reference's 1e-6 ridge, workflow_model_stream.py:902).  Eigenvalues ascending; the matrix is returned as U^T
  *     row-major (row k = k-th eigenvector = numpy.linalg.eigh(a)[1].T).  ut_f32_* receive the f32-rounded U^T the
  *     scan consumes (jxb_model_create[_dev]). */
+/* Devices for the eigendecomposition: 0 / 1 (default) = one cusolverDnXsyevd call on the caller's device; k > 1 =
+ * cusolverMgSyevd over the first k visible devices (1-D block-cyclic column panels, peer copies over NVLink).
+ * n > 46,340 always takes the cusolverMg path (cusolverDnXsyevd rejects n*n >= 2^31), on one device unless k says more. */
+void jxb_set_eigh_devices(int n_devices);
 int jxb_eigh(int device, size_t n, const double* a_host, double diag_shift, double* evals_host,
              double* ut_host /* nullable */, float* ut_f32_host /* nullable */);
 /* In place on the device: a_dev is overwritten by U^T.  Synchronises `stream` once (convergence flag); the

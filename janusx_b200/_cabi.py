@@ -97,6 +97,8 @@ SYMBOLS = {
     "jxb_set_thread_solve_min_rows": (None, [C.c_size_t]),
     "jxb_set_big_solve_kernel": (None, [C.c_int]),
     "jxb_set_stream_overlap": (None, [C.c_int, C.c_size_t]),
+    "jxb_set_generic_divide": (None, [C.c_int]),
+    "jxb_selftest_rcp": (C.c_int, [C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_uint64)]),
     "jxb_last_stage_ms8": (C.c_int, [_vp, _pf]),
     "jxb_scan_bed_to_tsv": (C.c_int, [_vp, C.POINTER(BedScanCfg), _psz, PROGRESS_CB, _vp]),
     "jxb_format_row": (C.c_size_t, [C.c_char_p, C.c_size_t, C.c_char_p, C.c_int64, C.c_char_p, C.c_char_p,
@@ -114,6 +116,7 @@ SYMBOLS = {
     "jxb_grm_destroy": (None, [_vp]),
     "jxb_vcf_to_plink": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, _psz, _psz]),
     "jxb_grm_eigh": (C.c_int, [_vp, C.c_double, _vp, _vp]),
+    "jxb_set_eigh_devices": (None, [C.c_int]),
     "jxb_eigh": (C.c_int, [C.c_int, C.c_size_t, _vp, C.c_double, _vp, _vp, _vp]),
     "jxb_eigh_dev": (C.c_int, [C.c_int, C.c_size_t, _vp, C.c_double, _vp, _vp, _vp]),
 }

@@ -48,7 +48,8 @@ static int g_timing = 0;
 static int g_rotate_variant = 3;
 static size_t g_thread_solve_min_rows = 32768;   // batches at least this large use the large-batch solve kernels
 static int g_big_solve_kernel = 0;               // 0 = lane-per-SNP with refill (row-major block), 1 = thread-per-SNP (SNP-minor)
-static int g_stream_overlap = 1;                 // 1 = large additive LMM/LMM2 batches rotate and solve concurrently (scan_streamed)
+static int g_stream_overlap = 0;                 // 1 = large additive LMM/LMM2 batches rotate and solve concurrently (scan_streamed);
+                                                 // off by default: both kernels are bound by the shared-memory pipe (profiles/README.md)
 static size_t g_stream_slab_rows = 8192;         // rows per rotation slab of the streamed scan (multiple of 256)
 
 void set_error(const std::string& msg) { g_err = msg; }
@@ -335,7 +336,8 @@ int scan_streamed(jxb_model* h, size_t nk, bool has_missing, const jxb_solve_cfg
         rc = launch_row_ssq_publish(m, m.rot, m.ldc, r0, r1, sync, m.stream);
         note_launch(2);
         if (rc) return rc;
-        if (r0 == 0) {
+        // g_stream_overlap == 2 (diagnostic): the same slim kernels, but the solve starts after the LAST slab
+        if (g_stream_overlap == 2 ? r1 == nk : r0 == 0) {
             JXB_CUDA_OK(cudaEventRecord(h->ev_slab0, m.stream));
             JXB_CUDA_OK(cudaStreamWaitEvent(h->stream2, h->ev_slab0, 0));
             tick(h, 8, h->stream2);
@@ -555,6 +557,7 @@ int scan_device_stages(jxb_model* h, const uint8_t* packed_dev, size_t bps, size
 
 // stage timers of the last scan from the recorded events (call after the stream has been synchronised)
 void collect_stage_ms(jxb_model* h) {
+    h->stage_ms[7] = h->last_streamed ? 1.f : 0.f;     // reported with or without timers
     if (g_timing && h->timing_ready) {
     for (int i = 0; i < 8; ++i) h->stage_ms[i] = 0.f;
     auto span = [&](int a, int b) -> float {
@@ -611,8 +614,18 @@ void jxb_set_timing(int on) { g_timing = on; }
 void jxb_set_rotate_variant(int variant) { g_rotate_variant = variant; }
 void jxb_set_thread_solve_min_rows(size_t rows) { g_thread_solve_min_rows = rows; }
 void jxb_set_big_solve_kernel(int variant) { g_big_solve_kernel = variant == 1 ? 1 : 0; }
+void jxb_set_generic_divide(int on) { g_force_generic_divide = on ? 1 : 0; }
+
+int jxb_selftest_rcp(size_t count, int lo_exp, int hi_exp, uint64_t* mismatches) {
+    if (!mismatches) return fail(-2, "null argument");
+    unsigned long long v = 0;
+    int rc = rcp_selftest(count, lo_exp, hi_exp, &v);
+    *mismatches = (uint64_t)v;
+    return rc;
+}
+
 void jxb_set_stream_overlap(int on, size_t slab_rows) {
-    g_stream_overlap = on ? 1 : 0;
+    g_stream_overlap = on == 2 ? 2 : (on ? 1 : 0);
     if (slab_rows) g_stream_slab_rows = slab_rows;
 }
 

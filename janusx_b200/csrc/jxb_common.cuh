@@ -114,6 +114,8 @@ int launch_solve_thread(Model& m, const float* rotT, size_t ldr, size_t max_rows
                         const SolveParams& sp, double* out, int out_cols, int32_t* evals, cudaStream_t st);
 int launch_solve_lane(Model& m, const float* rot, size_t ldc, size_t max_rows, const int32_t* n_rows_dev,
                       const SolveParams& sp, double* out, int out_cols, int32_t* evals, int32_t* queue, cudaStream_t st);
+int rcp_selftest(size_t count, int lo_exp, int hi_exp, unsigned long long* mismatches_host);
+extern int g_force_generic_divide;
 // streamed scan: solve while later row slabs are still being rotated (k3_solve.cu / cabi.cu scan_streamed)
 int ensure_solve_lane_buffers(Model& m, size_t max_rows, cudaStream_t st);
 int launch_row_ssq_publish(Model& m, const float* rot, size_t ldc, size_t row0, size_t row1, int32_t* sync, cudaStream_t st);

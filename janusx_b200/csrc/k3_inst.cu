@@ -53,22 +53,28 @@ int JXB_CAT(k3_launch_solve_thread_p, JXB_P)(const k3::ModelView& mv, const floa
     return 0;
 }
 
+// fast_rcp: every s_i + lambda of the search interval is inside rcp_fast's range (checked by the caller)
 int JXB_CAT(k3_launch_solve_lane_p, JXB_P)(const k3::ModelView& mv, int sms, const float* rot, size_t ldc, int max_rows,
                                            const int32_t* n_rows_dev, const SolveParams& sp, double* out, int out_cols,
                                            int32_t* evals, const void* log_table, double* ssq, int32_t* queue,
-                                           cudaStream_t st) {
+                                           int fast_rcp, cudaStream_t st) {
     constexpr int kSmem = 4 * (int)sizeof(k3::ThreadTile<JXB_P>);
     constexpr int kPerSm = (JXB_P <= 4) ? JXB_K3T_MINB : 3;
     static bool attr = false;
     if (!attr) {
-        cudaFuncSetAttribute(k3::solve_lane_kernel<JXB_P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+        cudaFuncSetAttribute(k3::solve_lane_kernel<JXB_P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+        cudaFuncSetAttribute(k3::solve_lane_kernel<JXB_P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
         attr = true;
     }
     k3::row_ssq_kernel<<<sms * 8, 256, 0, st>>>(rot, ldc, mv.n, max_rows, n_rows_dev, ssq);
     cudaMemsetAsync(queue, 0, sizeof(int32_t), st);
     const int blocks = std::min((max_rows + 127) / 128, sms * kPerSm);   // persistent: lanes refill from the queue
-    k3::solve_lane_kernel<JXB_P><<<blocks, 128, kSmem, st>>>(mv, rot, ldc, max_rows, n_rows_dev, sp, out, out_cols, evals,
-                                                            (const k3::LogTable*)log_table, ssq, queue);
+    if (fast_rcp)
+        k3::solve_lane_kernel<JXB_P, true><<<blocks, 128, kSmem, st>>>(mv, rot, ldc, max_rows, n_rows_dev, sp, out, out_cols, evals,
+                                                                      (const k3::LogTable*)log_table, ssq, queue);
+    else
+        k3::solve_lane_kernel<JXB_P, false><<<blocks, 128, kSmem, st>>>(mv, rot, ldc, max_rows, n_rows_dev, sp, out, out_cols, evals,
+                                                                       (const k3::LogTable*)log_table, ssq, queue);
     return 0;
 }
 

@@ -2,6 +2,8 @@
 // instantiations: k3_inst.cu compiled once per P; this unit holds the runtime-p and fixed-lambda kernels).
 #include "k3_solve.cuh"
 
+#include <cmath>
+
 namespace jxb {
 
 #define JXB_DECL_P(P)                                                                                          \
@@ -14,12 +16,14 @@ namespace jxb {
                                     const SolveParams&, double*, int, int32_t*, const void*, cudaStream_t);    \
     int k3_launch_solve_lane_p##P(const k3::ModelView&, int, const float*, size_t, int, const int32_t*,        \
                                   const SolveParams&, double*, int, int32_t*, const void*, double*, int32_t*,  \
-                                  cudaStream_t);                                                               \
+                                  int, cudaStream_t);                                                          \
     int k3_launch_solve_lane_stream_p##P(const k3::ModelView&, int, const float*, size_t, int, const SolveParams&, \
                                          double*, int, int32_t*, const void*, const double*, int32_t*, cudaStream_t); \
     int k3_solve_lane_stream_res_p##P(int*, int*);
 JXB_DECL_P(1) JXB_DECL_P(2) JXB_DECL_P(3) JXB_DECL_P(4) JXB_DECL_P(5) JXB_DECL_P(6) JXB_DECL_P(7) JXB_DECL_P(8)
 #undef JXB_DECL_P
+
+int g_force_generic_divide = 0;   // tests: compare the rcp_fast kernels with the compiler-divide kernels
 
 namespace {
 
@@ -144,7 +148,15 @@ int launch_solve_lane(Model& m, const float* rot, size_t ldc, size_t max_rows, c
     }
     const ModelView mv = view_of(m);
     const int sms = sm_count(m.device);
-#define L_STATIC(P) k3_launch_solve_lane_p##P(mv, sms, rot, ldc, (int)max_rows, n_rows_dev, sp, out, out_cols, evals, m.log_table, m.ssq, queue, st)
+    // rcp_fast (k3_solve.cuh) needs every s_i + lambda of the Brent interval to be positive and inside [1e-290, 1e290];
+    // fl(s_i + lambda) is monotone in both, so the extreme eigenvalues and the interval ends decide
+    int fast = 0;
+    if (!m.s_host.empty() && !g_force_generic_divide) {
+        const auto mm = std::minmax_element(m.s_host.begin(), m.s_host.end());
+        const double lo = *mm.first + pow(10.0, std::min(sp.low, sp.high)), hi = *mm.second + pow(10.0, std::max(sp.low, sp.high));
+        fast = std::isfinite(lo) && std::isfinite(hi) && lo >= 1e-290 && hi <= 1e290;
+    }
+#define L_STATIC(P) k3_launch_solve_lane_p##P(mv, sms, rot, ldc, (int)max_rows, n_rows_dev, sp, out, out_cols, evals, m.log_table, m.ssq, queue, fast, st)
 #define L_DYN() (void)0
     JXB_DISPATCH_P((int)m.p, L_STATIC, L_DYN)
 #undef L_STATIC
@@ -201,6 +213,19 @@ int solve_lane_stream_resources(size_t p, int* regs, int* smem) {
         case 4: return k3_solve_lane_stream_res_p4(regs, smem);
         default: return -1;
     }
+}
+
+// rcp_fast against 1.0 / x on `count` pseudo-random doubles with exponents in [lo_exp, hi_exp]; returns mismatches
+int rcp_selftest(size_t count, int lo_exp, int hi_exp, unsigned long long* mismatches_host) {
+    unsigned long long* d = nullptr;
+    JXB_CUDA_OK(cudaMalloc((void**)&d, sizeof(unsigned long long)));
+    JXB_CUDA_OK(cudaMemset(d, 0, sizeof(unsigned long long)));
+    const int threads = 256, blocks = 148 * 8, per = (int)std::max<size_t>(1, count / ((size_t)threads * blocks));
+    rcp_selftest_kernel<<<blocks, threads>>>(0x1234567ull, per, (double)lo_exp, (double)hi_exp, d);
+    cudaError_t e = cudaMemcpy(mismatches_host, d, sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(-100, cudaGetErrorString(e));
+    return 0;
 }
 
 int launch_null_fit(const Model& m, int kind, double low, double high, int max_iter, double tol, int has_init,

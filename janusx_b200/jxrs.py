@@ -447,7 +447,7 @@ def set_big_solve_kernel(variant: int) -> None:
 def set_stream_overlap(on: bool, slab_rows: int = 0) -> None:
     """Streamed scan (default on): rotate large batches in slabs while one persistent solve kernel consumes the rotated
     rows, so the tensor pipe and the FP64 pipe run concurrently.  slab_rows = 0 keeps the current slab size (8192)."""
-    lib().jxb_set_stream_overlap(1 if on else 0, int(slab_rows))
+    lib().jxb_set_stream_overlap(int(on) if on in (0, 1, 2) else (1 if on else 0), int(slab_rows))
 
 
 def clear_model_cache() -> None:

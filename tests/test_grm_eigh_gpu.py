@@ -102,6 +102,29 @@ def test_eigh_matches_lapack_properties(jx, oracle):
         jx.rust_eigh_from_array_f64(np.zeros((2, 3)))
 
 
+def test_eigh_cusolvermg_path(jx, monkeypatch):
+    """The eigensolver behind n > 46,340 (BASELINE configs[3]) and behind jxb_set_eigh_devices(k > 1): cusolverMgSyevd on
+    block-cyclic column panels.  Exercised here at small n on one device (forced) and, when the box has them, on two
+    devices: eigenvalues and the reconstruction match LAPACK like the single-call path."""
+    import torch
+    from janusx_b200 import _cabi
+    rng = np.random.default_rng(9)
+    n = 777                                             # not a multiple of the 256-column panel
+    a = rng.normal(size=(n, n))
+    a = a @ a.T / n + 1e-6 * np.eye(n)
+    w_np = np.linalg.eigvalsh(a)
+    monkeypatch.setenv("JXB_EIGH_FORCE_MG", "1")
+    try:
+        for k in ([1, 2] if torch.cuda.device_count() >= 2 else [1]):
+            _cabi.lib().jxb_set_eigh_devices(k)
+            w, v = jx.rust_eigh_from_array_f64(a)[:2]
+            assert np.all(np.diff(w) >= 0) and np.abs(w - w_np).max() <= 1e-12 * np.abs(w_np).max()
+            assert np.abs(v.T @ v - np.eye(n)).max() <= 1e-11
+            assert np.abs((v * w) @ v.T - a).max() <= 1e-11 * np.abs(a).max()
+    finally:
+        _cabi.lib().jxb_set_eigh_devices(0)
+
+
 def test_grm_eigh_scan_pipeline_on_device(jx, oracle):
     """packed rows -> GRM -> eigh (chained on the device) -> null model -> scan, against the oracle run on the same
     spectral decomposition."""

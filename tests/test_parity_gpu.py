@@ -263,9 +263,10 @@ def test_packed_array_entry_points_and_tsv_writer(jx, oracle, tmp_path):
     got2 = jx.lmm_reml_assoc_packed_f32(case.packed[idx], n, flip, af[idx], case.s, nm["xcov"], nm["y"], nm["ut"],
                                         low=nm["low"], high=nm["high"], nullml=nm["ml0"], init_log10_lbd=l10)
     assert np.array_equal(got, got2, equal_nan=True)
-    with pytest.raises(RuntimeError, match="differs from the allele frequency"):
-        jx.lmm_reml_assoc_packed_f32(case.packed[idx], n, flip, af[idx] * np.float32(0.5), case.s, nm["xcov"], nm["y"],
-                                     nm["ut"], low=nm["low"], high=nm["high"])
+    # a row_maf that is not the frequency over these samples is used as given (test_prepared_row_maf_and_flip_are_used_as_given)
+    got3 = jx.lmm_reml_assoc_packed_f32(case.packed[idx], n, flip, af[idx] * np.float32(0.5), case.s, nm["xcov"], nm["y"],
+                                        nm["ut"], low=nm["low"], high=nm["high"])
+    assert got3.shape == (idx.size, 3)
     with pytest.raises(RuntimeError, match="packed second dimension mismatch"):
         jx.lmm_reml_assoc_packed_f32(case.packed[idx][:, :-1], n, flip, af[idx], case.s, nm["xcov"], nm["y"], nm["ut"])
     # to_tsv: same numbers, reference row format; metadata from arrays or from the BIM
@@ -603,6 +604,17 @@ def test_full_size_n20000_parity_sample(jx, oracle):
         np.testing.assert_allclose(out[:, 4], want[:, 4], rtol=1e-10)
 
 
+def test_rcp_fast_equals_ieee_divide(jx):
+    """The branch-free reciprocal of the large-batch solve kernels against `1.0 / x` on 2^26 values per exponent band
+    (random and extreme mantissas): zero differing bit patterns inside the range the host admits it for."""
+    import ctypes as C
+    lib = jx._cabi.lib()
+    for lo, hi in ((-30, 30), (-960, -900), (900, 960), (-1, 1)):
+        bad = C.c_uint64(123)
+        jx._cabi.check(lib.jxb_selftest_rcp(1 << 26, lo, hi, C.byref(bad)))
+        assert bad.value == 0, (lo, hi, bad.value)
+
+
 def test_prepared_row_maf_and_flip_are_used_as_given(jx, oracle, tmp_path):
     """Prepared row metadata as the reference consumes it (src/decode/decode.rs:163-219, src/stats/lmm.rs:1237-1262):
     `row_maf` is the imputation frequency even when it is NOT the frequency over the scanned samples
@@ -655,7 +667,7 @@ def test_full_batch_at_full_size_sampled_parity(jx, oracle, n, model):
     then -fvlmm on the same batch) and configs[3] (n = 50,000, -lmm): rows sampled from the start, middle and end of the
     batch are checked against the oracle, which catches 32-bit index overflow in any kernel (rows x n exceeds 2^31 at
     n = 50,000).  The n = 20,000 batch runs the streamed scan (rotation slabs under the persistent solve kernel) and
-    is repeated with the overlap switched off: bit-identical."""
+    is repeated with the compiler's divide and through the streamed (overlapped) scan: bit-identical."""
     import sys
     from pathlib import Path
     import torch
@@ -706,16 +718,24 @@ def test_full_batch_at_full_size_sampled_parity(jx, oracle, n, model):
         want, ev_o = oracle.lmm_reml_chunk_f32(s_np, xo, yo[:, 0], lo, hi, rot_o, 30, 1e-2, return_evals=True)
         assert_results_close(got, want)
         assert np.array_equal(ev[pos[picks]], ev_o)             # the same Brent path, evaluation for evaluation
+    assert not streamed
     if n <= 24000:
-        assert streamed, "the n = 20,000 batch should take the streamed (overlapped) scan"
-        # rotate-then-solve on the same batch: same kernels' arithmetic, bit-identical rows
-        jx.set_stream_overlap(False)
+        # the same batch with the compiler-generated divide instead of rcp_fast, and through the streamed scan (rotation
+        # slabs under one persistent solve kernel): same arithmetic, bit-identical rows
+        jx._cabi.lib().jxb_set_generic_divide(1)
+        try:
+            mdl.scan_packed_dev(pk.data_ptr(), rows, bps, n, None, **kw)
+            keep1, af1, missing1, out1, ev1 = mdl.scan_fetch(rows, cols)
+        finally:
+            jx._cabi.lib().jxb_set_generic_divide(0)
+        assert np.array_equal(out, out1, equal_nan=True) and np.array_equal(ev, ev1)
+        jx.set_stream_overlap(True)
         try:
             mdl.scan_packed_dev(pk.data_ptr(), rows, bps, n, None, **kw)
             keep2, af2, missing2, out2, ev2 = mdl.scan_fetch(rows, cols)
-            assert mdl.stage_ms()["streamed"] == 0
+            assert mdl.stage_ms()["streamed"] == 1
         finally:
-            jx.set_stream_overlap(True)
+            jx.set_stream_overlap(False)
         assert np.array_equal(keep, keep2) and np.array_equal(out, out2, equal_nan=True) and np.array_equal(ev, ev2)
         # BASELINE.json configs[4]: -fvlmm (fixed lambda = null lambda) on the same full batch
         cols_f = mdl.scan_packed_dev(pk.data_ptr(), rows, bps, n, None, mode="fvlmm", log10_lbd=l10)
