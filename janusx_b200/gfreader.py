@@ -227,3 +227,106 @@ class BedChunkReader:
         if m == 0:
             return None
         return np.concatenate(blocks), sites, np.concatenate(afs), np.concatenate(misses)
+
+
+# ------------------------------------------------------------------------------------------------------
+# prepared row statistics of one trait's samples (second half)
+# ------------------------------------------------------------------------------------------------------
+def _meta_row_decisions(missing, het, hom_alt, n: int, maf_thr, miss_thr, het_thr):
+    """prepare_bed_logic_meta_owned... row closure (src/io/gfreader.rs:5378-5424) on integer counts:
+    missing_rate f32 = missing / n (packed_row_stats_from_counts, :1911-1929); alt_freq f32 = alt_sum / (2 f32 * non_missing);
+    het rate compared in f64; maf test min(af, 1 - af) >= maf_thr in f32.  -> (keep, missing_rate f32, alt_freq f32)."""
+    missing = np.asarray(missing, dtype=np.int64)
+    het = np.asarray(het, dtype=np.int64)
+    hom = np.asarray(hom_alt, dtype=np.int64)
+    maf_t, miss_t, het_t = np.float32(maf_thr), np.float32(miss_thr), np.float32(het_thr)
+    non_missing = np.maximum(n - missing, 0)
+    alt_sum = het + 2 * hom
+    with np.errstate(divide="ignore", invalid="ignore"):
+        miss_rate = ((n - non_missing).astype(np.float32) / np.float32(n)) if n > 0 else np.zeros(missing.shape, np.float32)
+        alt_freq = alt_sum.astype(np.float32) / (np.float32(2.0) * non_missing.astype(np.float32))
+        alt_freq = np.where(non_missing > 0, alt_freq, np.float32(0.0)).astype(np.float32)
+        empty = non_missing == 0
+        keep = ~(miss_rate > miss_t)
+        keep &= ~(empty & ~(maf_t <= np.float32(0.0)))
+        if het_t > np.float32(0.0):                                   # apply_het_filter = het_threshold > 0
+            het_rate = het.astype(np.float64) / non_missing.astype(np.float64)
+            keep &= ~(~empty & (het_rate > np.float64(het_t)))
+        keep &= empty | (np.minimum(alt_freq, np.float32(1.0) - alt_freq) >= maf_t)
+    return keep, miss_rate.astype(np.float32), alt_freq
+
+
+def _bed_counts_selected(prefix: str, sample_indices, device: int, batch_rows: int = 1 << 16):
+    """Integer genotype counts (missing, het, hom_alt) of every BED row over the selected samples, on the device
+    (count_packed_row_counts[_selected_with_excluded], src/io/gfreader.rs:1378-1528)."""
+    import os
+    prefix = str(prefix)
+    for ext in (".bed", ".bim", ".fam"):
+        if prefix.lower().endswith(ext):
+            prefix = prefix[: -len(ext)]
+    with open(prefix + ".fam") as fh:
+        n_full = sum(1 for line in fh if line.strip())
+    if n_full == 0:
+        raise RuntimeError("no samples found in PLINK input")
+    sidx = None
+    if sample_indices is not None:
+        sidx = np.ascontiguousarray(np.asarray(sample_indices, dtype=np.int64).reshape(-1))
+        bad = (sidx < 0) | (sidx >= n_full)
+        if bad.any():
+            raise ValueError(f"sample index out of range: {int(sidx[bad][0])} for n_samples={n_full}")
+    n = n_full if sidx is None else int(sidx.shape[0])
+    bps = (n_full + 3) // 4
+    size = os.path.getsize(prefix + ".bed")
+    raw = np.memmap(prefix + ".bed", dtype=np.uint8, mode="r")
+    if size < 3 or bytes(raw[:3]) != b"\x6c\x1b\x01":
+        raise RuntimeError("only SNP-major BED supported")
+    if (size - 3) % bps:
+        raise RuntimeError(f"BED payload length {size - 3} not a multiple of {bps}")
+    m = (size - 3) // bps
+    packed = raw[3:].reshape(m, bps)
+    counts = np.zeros((m, 3), dtype=np.int64)
+    mdl = DeviceModel(np.ones(max(n, 1)), np.ones((max(n, 1), 1)), np.zeros(max(n, 1)), None, device=device)
+    try:
+        for r0 in range(0, m, batch_rows):
+            c, _, _, _ = mdl.decode_packed(np.ascontiguousarray(packed[r0:r0 + batch_rows]), n_full, sample_idx=sidx,
+                                           maf_thr=0.0, miss_thr=1.0, het_thr=0.0, want_g=False)
+            counts[r0:r0 + c.shape[0]] = c[:, :3]
+    finally:
+        mdl.close()
+    return prefix, n_full, n, m, counts
+
+
+def prepare_bed_logic_meta_selected(prefix, sample_indices=None, maf_threshold=0.0, max_missing_rate=1.0, het_threshold=1.0,
+                                    snps_only=False, mmap_window_mb=None, threads=1, device: int = 0):
+    """src/io/gfreader.rs:7119-7232 -> (row_idx i64[k], miss f32[k], af f32[k], row_flip bool[k], site_keep bool[m],
+    n_samples, n_snps_total): the per-trait prepared row statistics the reference computes once per trait and hands to
+    lmm_reml_assoc_bed_to_tsv_f32 as row_indices / row_missing / row_maf / row_flip (assoc/workflow.py:8870-8888).
+    `af` is the ALT frequency over the selected samples (never folded); row_flip is all False (gfreader.rs:5468-5471)."""
+    if not (0.0 <= maf_threshold <= 0.5):
+        raise ValueError("maf_threshold must be within [0, 0.5]")
+    if not (0.0 <= max_missing_rate <= 1.0):
+        raise ValueError("max_missing_rate must be within [0, 1.0]")
+    if not (0.0 <= het_threshold <= 1.0):
+        raise ValueError("het_threshold must be within [0, 1.0]")
+    require_gpu()
+    prefix, n_full, n, m, counts = _bed_counts_selected(prefix, sample_indices, device)
+    keep, miss_rate, alt_freq = _meta_row_decisions(counts[:, 0], counts[:, 1], counts[:, 2], n, maf_threshold,
+                                                    max_missing_rate, het_threshold)
+    if snps_only:
+        with open(prefix + ".bim") as fh:
+            simple = np.fromiter((_simple_allele(t[4]) and _simple_allele(t[5]) for t in (ln.split() for ln in fh)),
+                                 dtype=bool, count=m)
+        keep &= simple
+    if not keep.any():
+        raise RuntimeError("No SNPs left after packed BED filtering. Please relax thresholds.")
+    row_idx = np.nonzero(keep)[0].astype(np.int64)
+    return (row_idx, np.ascontiguousarray(miss_rate[keep]), np.ascontiguousarray(alt_freq[keep]),
+            np.zeros(row_idx.shape[0], dtype=bool), keep, n_full, m)
+
+
+def prepare_bed_logic_keep_mask(prefix, sample_indices=None, maf_threshold=0.0, max_missing_rate=1.0, het_threshold=1.0,
+                                snps_only=False, mmap_window_mb=None, threads=1, device: int = 0):
+    """src/io/gfreader.rs:7234-7300 -> (site_keep bool[m], n_samples, n_snps_total)."""
+    out = prepare_bed_logic_meta_selected(prefix, sample_indices, maf_threshold, max_missing_rate, het_threshold, snps_only,
+                                          mmap_window_mb, threads, device)
+    return out[4], out[5], out[6]

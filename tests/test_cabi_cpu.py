@@ -245,3 +245,28 @@ def test_packed_entry_point_validation_and_writer_text_paths(tmp_path):
     chrom, pos, snp, a0, a1 = cols(str(tmp_path / "p"), None)
     assert (chrom, pos, snp, a0, a1) == (["1", "2"], [100, 0], ["rs1", "."], ["A", "C"], ["G", "T"])
     assert cols(str(tmp_path / "p"), [1])[2] == ["."]
+
+
+def test_prepared_meta_row_decisions_host_logic():
+    """prepare_bed_logic_meta_selected's row closure (src/io/gfreader.rs:5378-5424) on integer counts: f32 missing rate and
+    ALT frequency, f64 het-rate comparison, `non_missing == 0` kept only without a MAF threshold."""
+    from janusx_b200.gfreader import _meta_row_decisions
+    rng = np.random.default_rng(0)
+    n = 137
+    miss, het, hom = rng.integers(0, 40, 500), rng.integers(0, 60, 500), rng.integers(0, 37, 500)
+    miss[::50], het[::50], hom[::50] = n, 0, 0
+    for maf_t, miss_t, het_t in ((0.05, 0.2, 0.4), (0.0, 1.0, 0.0), (0.02, 0.05, 1.0)):
+        k, mr, af = _meta_row_decisions(miss, het, hom, n, maf_t, miss_t, het_t)
+        for i in range(500):
+            nm, alt = n - miss[i], het[i] + 2 * hom[i]
+            mr_i = np.float32(n - nm) / np.float32(n)
+            af_i = np.float32(alt) / (np.float32(2.0) * np.float32(nm)) if nm > 0 else np.float32(0)
+            if mr_i > np.float32(miss_t):
+                keep = False
+            elif nm == 0:
+                keep = np.float32(maf_t) <= 0
+            elif np.float32(het_t) > 0 and (het[i] / nm) > float(np.float32(het_t)):
+                keep = False
+            else:
+                keep = min(af_i, np.float32(1) - af_i) >= np.float32(maf_t)
+            assert keep == k[i] and mr_i == mr[i] and af_i == af[i], (i, maf_t)

@@ -115,3 +115,36 @@ def test_route_b_chain_matches_oracle(jx, oracle, tmp_path):
     want3 = oracle.lmm_assoc_chunk_from_snp_f32(fv.S, fv.Xcov, fv.y[:, 0], float(np.log10(fv.lbd_null)), g_o[:64], fv.Dh)
     want3 = want3[0] if isinstance(want3, tuple) else want3
     assert_results_close(res3, want3)
+
+
+def test_prepared_row_statistics_feed_the_bed_scan(jx, oracle, tmp_path):
+    """The default CLI route of the reference: prepare_bed_logic_meta_selected (src/io/gfreader.rs:7119-7232) once per
+    trait over the trait's samples, then lmm_reml_assoc_bed_to_tsv_f32 with row_indices / row_missing / row_maf /
+    row_flip (assoc/workflow.py:8870-8888).  Counts come from the device; the TSV equals the plain thresholded scan."""
+    from janusx_b200 import synth
+    from conftest import make_problem, null_model
+    case = make_problem(n=260, m=700, q=1, seed=77, missing_rate=0.03)
+    nm = null_model(oracle, case)
+    prefix = str(tmp_path / "p")
+    synth.write_plink(prefix, case.packed, case.n)
+    row_idx, miss, af, flip, site_keep, n_full, n_snps = jx.prepare_bed_logic_meta_selected(prefix, None, 0.02, 0.05, 1.0)
+    keep_o, af_o, mr_o, _ = oracle.count_qc_block(case.packed, case.n, None, 0.02, 0.05, 1.0)
+    assert (n_full, n_snps) == (case.n, 700) and np.array_equal(site_keep, keep_o)
+    assert np.array_equal(row_idx, np.nonzero(keep_o)[0]) and not flip.any()
+    assert np.array_equal(af.view(np.uint32), af_o[keep_o].view(np.uint32))
+    assert np.array_equal(miss.view(np.uint32), mr_o[keep_o].view(np.uint32))
+    mask, n2, m2 = jx.prepare_bed_logic_keep_mask(prefix, None, 0.02, 0.05, 1.0)
+    assert np.array_equal(mask, keep_o) and (n2, m2) == (case.n, 700)
+    args = (case.s, nm["xcov"], nm["y"], nm["ut"], 0.02, 0.05, 1.0)
+    rows = jx.lmm_reml_assoc_bed_to_tsv_f32(prefix, str(tmp_path / "a.tsv"), *args, low=nm["low"], high=nm["high"])
+    rows_p = jx.lmm_reml_assoc_bed_to_tsv_f32(prefix, str(tmp_path / "b.tsv"), *args, low=nm["low"], high=nm["high"],
+                                              row_indices=row_idx, row_flip=flip, row_missing=miss, row_maf=af)
+    assert rows == rows_p == int(keep_o.sum())
+    assert (tmp_path / "a.tsv").read_bytes() == (tmp_path / "b.tsv").read_bytes()
+    # a sample subset: the statistics are those of the subset
+    sub = np.arange(5, case.n, 2, dtype=np.int64)
+    r2 = jx.prepare_bed_logic_meta_selected(prefix, sub, 0.05, 0.1, 1.0)
+    k2, af2, mr2, _ = oracle.count_qc_block(case.packed, case.n, sub, 0.05, 0.1, 1.0)
+    assert np.array_equal(r2[4], k2) and np.array_equal(r2[2].view(np.uint32), af2[k2].view(np.uint32))
+    with pytest.raises(ValueError, match="sample index out of range"):
+        jx.prepare_bed_logic_meta_selected(prefix, np.array([0, case.n]))
