@@ -174,6 +174,16 @@ int jxb_decode_packed_prepared(jxb_model* m, const uint8_t* packed_host, size_t 
                                const int64_t* sample_idx_host, const uint8_t* keep_host, const float* af_host,
                                int genetic_model, float* g_host, size_t* n_kept);
 
+/* Decode with caller-supplied row means and NO centring: BedChunkReaderFromMeta.next_chunk_prepared
+ * (src/io/gfreader.rs:7623-7730): value LUT [(0 - mean), 0 (missing), (1 - mean), (2 - mean)] in f32, mean = 2 * ALT
+ * frequency from the shared per-trait metadata.  Every supplied row is decoded.  g_host f32[rows, n]. */
+int jxb_decode_packed_meta(jxb_model* m, const uint8_t* packed_host, size_t bps, size_t rows, size_t n_full,
+                           const int64_t* sample_idx_host, const float* row_mean_host, float* g_host);
+
+/* Debug: rows [row0, row0 + rows) of the rotated block of the last scan, INCLUDING the zero padding of every row
+ * (rot_host f32[rows, round_up(n, 32)], compacted row order).  Parity tests compare it with the oracle's rotation. */
+int jxb_debug_fetch_rot(jxb_model* m, size_t row0, size_t rows, float* rot_host);
+
 /* Per-stage device timers of the last jxb_scan_packed* call, milliseconds:
  * [0]=count+qc+compact [1]=decode [2]=rotate [3]=solve [4]=h2d [5]=d2h.  (The reference's
  * JX_LMM_UNIFIED_STAGE_TIMING, src/stats/lmm.rs:2711-2742.)  Enabled by jxb_set_timing(1). */
@@ -201,6 +211,9 @@ void jxb_set_big_solve_kernel(int variant);
  * (tests compare the two); jxb_selftest_rcp compares `count` pseudo-random values with binary exponents in
  * [lo_exp, hi_exp] (extreme mantissas included) and returns the number of differing bit patterns. */
 void jxb_set_generic_divide(int on);
+/* fixed-lambda batches with at least this many rows use the lane-per-SNP kernel (one HBM-bound pass over the rotated
+ * block; default 4096); smaller ones the warp-per-SNP kernel.  Same ordered sums, identical results. */
+void jxb_set_fixed_lane_min_rows(size_t rows);
 int jxb_selftest_rcp(size_t count, int lo_exp, int hi_exp, uint64_t* mismatches);
 /* Streamed scan (default on): large additive LMM / LMM2 batches are rotated in slabs of `slab_rows` rows (0 = keep the
  * current value, default 8192) while ONE persistent solve kernel consumes the rows already rotated -- the tensor pipe

@@ -89,6 +89,8 @@ SYMBOLS = {
                                     _vp, _vp, _psz]),
     "jxb_decode_packed_prepared": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_size_t, _vp, _vp, _vp, C.c_int, _vp,
                                              _psz]),
+    "jxb_decode_packed_meta": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_size_t, _vp, _vp, _vp]),
+    "jxb_debug_fetch_rot": (C.c_int, [_vp, C.c_size_t, C.c_size_t, _vp]),
     "jxb_set_timing": (None, [C.c_int]),
     "jxb_last_stage_ms": (C.c_int, [_vp, _pf]),
     "jxb_model_stream": (_vp, [_vp]),
@@ -98,6 +100,7 @@ SYMBOLS = {
     "jxb_set_big_solve_kernel": (None, [C.c_int]),
     "jxb_set_stream_overlap": (None, [C.c_int, C.c_size_t]),
     "jxb_set_generic_divide": (None, [C.c_int]),
+    "jxb_set_fixed_lane_min_rows": (None, [C.c_size_t]),
     "jxb_selftest_rcp": (C.c_int, [C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_uint64)]),
     "jxb_last_stage_ms8": (C.c_int, [_vp, _pf]),
     "jxb_scan_bed_to_tsv": (C.c_int, [_vp, C.POINTER(BedScanCfg), _psz, PROGRESS_CB, _vp]),

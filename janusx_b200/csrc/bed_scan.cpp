@@ -65,10 +65,85 @@ size_t fmt_exp(char* buf, size_t cap, double v, int prec) {
     return (size_t)snprintf(buf, cap, "%se%d", tmp, ex);
 }
 
+// Pinned staging buffers are kept between calls (page-locking hundreds of MB costs more than a small scan):
+// a process-wide pool of at most kPoolMax idle buffers.
+struct PinnedPool {
+    static constexpr size_t kPoolMax = 4;
+    std::mutex mu;
+    std::vector<std::pair<uint8_t*, size_t>> idle;
+    uint8_t* acquire(size_t bytes, size_t* cap) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            size_t best = idle.size();
+            for (size_t i = 0; i < idle.size(); ++i)
+                if (idle[i].second >= bytes && (best == idle.size() || idle[i].second < idle[best].second)) best = i;
+            if (best != idle.size()) {
+                uint8_t* p = idle[best].first;
+                *cap = idle[best].second;
+                idle.erase(idle.begin() + (long)best);
+                return p;
+            }
+        }
+        uint8_t* p = nullptr;
+        if (cudaHostAlloc((void**)&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return nullptr;
+        }
+        *cap = bytes;
+        return p;
+    }
+    void release(uint8_t* p, size_t cap) {
+        if (!p) return;
+        std::lock_guard<std::mutex> lk(mu);
+        if (idle.size() < kPoolMax) { idle.emplace_back(p, cap); return; }
+        // keep the larger buffers
+        size_t smallest = 0;
+        for (size_t i = 1; i < idle.size(); ++i) if (idle[i].second < idle[smallest].second) smallest = i;
+        if (idle[smallest].second < cap) { cudaFreeHost(idle[smallest].first); idle[smallest] = {p, cap}; }
+        else cudaFreeHost(p);
+    }
+};
+PinnedPool& pinned_pool() { static PinnedPool* g = new PinnedPool(); return *g; }
+
+// One BIM row as views into the memory-mapped .bim (no per-token allocation: at > 1 M SNPs/s the producer thread must
+// parse a line in well under a microsecond).  The mapping outlives every Site (it is released after the writer joins).
+struct Str {
+    const char* p = "";
+    uint32_t n = 0;
+};
 struct Site {
-    std::string chrom, snp, a0, a1;
+    Str chrom, snp, a0, a1;
     int64_t pos = 0;
 };
+
+inline bool is_ws(char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\n' || c == '\v' || c == '\f'; }
+
+// Rust str::parse::<i32>(): optional sign, decimal digits only, range-checked; failure -> 0
+int64_t parse_i32_or_zero(const char* s, size_t n) {
+    if (n == 0) return 0;
+    size_t i = 0;
+    bool neg = false;
+    if (s[0] == '+' || s[0] == '-') { neg = s[0] == '-'; i = 1; }
+    if (i >= n) return 0;
+    int64_t v = 0;
+    for (; i < n; ++i) {
+        if (s[i] < '0' || s[i] > '9') return 0;
+        v = v * 10 + (s[i] - '0');
+        if (v > 2147483648LL) return 0;
+    }
+    v = neg ? -v : v;
+    if (v < -2147483648LL || v > 2147483647LL) return 0;
+    return v;
+}
+
+bool simple_snp_allele(const char* a, size_t n) {
+    size_t b = 0, e = n;
+    while (b < e && is_ws(a[b])) ++b;
+    while (e > b && is_ws(a[e - 1])) --e;
+    if (e - b != 1) return false;
+    const char c = (char)toupper((unsigned char)a[b]);
+    return c == 'A' || c == 'C' || c == 'G' || c == 'T';
+}
 
 std::vector<std::string> split_ws(const std::string& line) {
     std::vector<std::string> out;
@@ -83,61 +158,63 @@ std::vector<std::string> split_ws(const std::string& line) {
     return out;
 }
 
-// Rust str::parse::<i32>(): optional sign, decimal digits only, range-checked; failure -> 0
-int64_t parse_i32_or_zero(const std::string& s) {
-    if (s.empty()) return 0;
-    size_t i = 0;
-    bool neg = false;
-    if (s[0] == '+' || s[0] == '-') { neg = s[0] == '-'; i = 1; }
-    if (i >= s.size()) return 0;
-    int64_t v = 0;
-    for (; i < s.size(); ++i) {
-        if (s[i] < '0' || s[i] > '9') return 0;
-        v = v * 10 + (s[i] - '0');
-        if (v > 2147483648LL) return 0;
-    }
-    v = neg ? -v : v;
-    if (v < -2147483648LL || v > 2147483647LL) return 0;
-    return v;
-}
-
-bool simple_snp_allele(const std::string& a) {
-    size_t b = 0, e = a.size();
-    while (b < e && isspace((unsigned char)a[b])) ++b;
-    while (e > b && isspace((unsigned char)a[e - 1])) --e;
-    if (e - b != 1) return false;
-    const char c = (char)toupper((unsigned char)a[b]);
-    return c == 'A' || c == 'C' || c == 'G' || c == 'T';
-}
-
+// BimChunkReader / parse_bim_line (src/io/gfcore.rs:112-302, 1426-1478) over a read-only mapping of the file
 struct BimReader {
-    std::ifstream in;
     std::string path;
+    const char* base = nullptr;
+    size_t size = 0, off = 0;
     size_t next_row = 0;
     bool open(const std::string& prefix) {
         path = prefix + ".bim";
-        in.open(path);
-        return in.good();
+        int fd = ::open(path.c_str(), O_RDONLY);
+        if (fd < 0) return false;
+        struct stat st;
+        if (fstat(fd, &st) != 0) { ::close(fd); return false; }
+        size = (size_t)st.st_size;
+        if (size) {
+            void* m = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (m == MAP_FAILED) { ::close(fd); return false; }
+            base = (const char*)m;
+            madvise(m, size, MADV_SEQUENTIAL);
+        }
+        ::close(fd);
+        return true;
     }
+    ~BimReader() { if (base && size) munmap((void*)base, size); }
     // returns 0 ok, 1 EOF, -1 malformed
     int next(Site& s, std::string& err) {
-        std::string line;
-        if (!std::getline(in, line)) return 1;
+        if (off >= size) return 1;
+        const char* line = base + off;
+        const char* eol = (const char*)memchr(line, '\n', size - off);
+        const size_t len = eol ? (size_t)(eol - line) : size - off;
+        off += len + (eol ? 1 : 0);
         ++next_row;
-        auto tok = split_ws(line);
-        if (tok.size() < 6) {
-            while (!line.empty() && isspace((unsigned char)line.back())) line.pop_back();
-            err = "Malformed BIM line at " + path + ":" + std::to_string(next_row) + ": " + line;
+        Str tok[6];
+        int nt = 0;
+        size_t i = 0;
+        while (i < len && nt < 6) {
+            while (i < len && is_ws(line[i])) ++i;
+            size_t j = i;
+            while (j < len && !is_ws(line[j])) ++j;
+            if (j > i) { tok[nt].p = line + i; tok[nt].n = (uint32_t)(j - i); ++nt; }
+            i = j;
+        }
+        if (nt < 6) {
+            size_t e = len;
+            while (e > 0 && is_ws(line[e - 1])) --e;
+            err = "Malformed BIM line at " + path + ":" + std::to_string(next_row) + ": " + std::string(line, e);
             return -1;
         }
         s.chrom = tok[0];
         s.snp = tok[1];
-        s.pos = parse_i32_or_zero(tok[3]);
+        s.pos = parse_i32_or_zero(tok[3].p, tok[3].n);
         s.a0 = tok[4];
         s.a1 = tok[5];
         return 0;
     }
 };
+
+size_t format_row_views(char* buf, size_t cap, const Site& s, float af, float miss_rate, const double* row, int out_cols);
 
 struct Batch {
     std::vector<Site> sites;      // per source row
@@ -194,13 +271,12 @@ struct Writer {
                     const Site& s = b->sites[r];
                     // lmm.rs:2667-2670: miss column = missing_count as f32 / n as f32
                     const float mr = n_model ? (float)b->missing[r] / (float)n_model : 0.0f;
-                    size_t len = jxb_format_row(buf.data(), buf.size(), s.chrom.c_str(), s.pos, s.snp.c_str(),
-                                                s.a0.c_str(), s.a1.c_str(), b->af[r], mr,
-                                                b->out.data() + i * b->out_cols, b->out_cols);
+                    size_t len = format_row_views(buf.data(), buf.size(), s, b->af[r], mr, b->out.data() + i * b->out_cols,
+                                                  b->out_cols);
                     if (len > buf.size()) {
                         buf.resize(len);
-                        len = jxb_format_row(buf.data(), buf.size(), s.chrom.c_str(), s.pos, s.snp.c_str(), s.a0.c_str(),
-                                             s.a1.c_str(), b->af[r], mr, b->out.data() + i * b->out_cols, b->out_cols);
+                        len = format_row_views(buf.data(), buf.size(), s, b->af[r], mr, b->out.data() + i * b->out_cols,
+                                               b->out_cols);
                     }
                     text.append(buf.data(), len);
                 }
@@ -249,16 +325,13 @@ const char* header_for(int out_cols) {
 
 // Bytes a row can need: the strings verbatim (chrom twice for the chrom_pos fallback name) plus nine numeric fields
 // (a `{:.4}` rendering of a huge finite double is ~315 characters) plus separators.
-static size_t format_row_need(const char* chrom, const char* snp, const char* a0, const char* a1) {
-    return 2 * strlen(chrom) + strlen(snp) + strlen(a0) + strlen(a1) + 9 * 336 + 64;
-}
+static size_t format_row_need(size_t chrom, size_t snp, size_t a0, size_t a1) { return 2 * chrom + snp + a0 + a1 + 9 * 336 + 64; }
 
 // Never writes past buf[cap-1].  Returns the row length when it fitted; otherwise a value > cap (the size that is
 // guaranteed to fit) and the buffer content is unspecified -- callers retry with a larger buffer.
-static size_t format_row_impl(char* buf, size_t cap, const char* chrom, int64_t pos, const char* snp,
-                              const char* a0, const char* a1, float af, float miss_rate, const double* row,
-                              int out_cols, bool resolve_name) {
-    const size_t need = format_row_need(chrom, snp, a0, a1);
+static size_t format_row_impl(char* buf, size_t cap, Str chrom, int64_t pos, Str snp, Str a0, Str a1, float af,
+                              float miss_rate, const double* row, int out_cols, bool resolve_name) {
+    const size_t need = format_row_need(chrom.n, snp.n, a0.n, a1.n);
     if (cap < need) return need > cap ? need : cap + 1;
     const double beta = row[0], se = row[1];
     const bool valid = std::isfinite(beta) && std::isfinite(se) && se > 0.0;
@@ -275,11 +348,11 @@ static size_t format_row_impl(char* buf, size_t cap, const char* chrom, int64_t 
     char* end = buf + cap;
     // snprintf reports the untruncated length: clamp so `w` can never leave the buffer
     auto adv = [&](size_t k) { const size_t room = (size_t)(end - w) - 1; w += k < room ? k : room; };
-    auto put_s = [&](const char* s) { const size_t k = strlen(s), room = (size_t)(end - w) - 1; const size_t c = k < room ? k : room; memcpy(w, s, c); w += c; };
+    auto put_s = [&](Str t) { const size_t room = (size_t)(end - w) - 1; const size_t c = t.n < room ? t.n : room; memcpy(w, t.p, c); w += c; };
     auto tab = [&]() { if (w < end - 1) *w++ = '\t'; };
     put_s(chrom); tab();
     adv((size_t)snprintf(w, (size_t)(end - w), "%lld", (long long)pos)); tab();
-    if (resolve_name && (snp[0] == '\0' || (snp[0] == '.' && snp[1] == '\0'))) {
+    if (resolve_name && (snp.n == 0 || (snp.n == 1 && snp.p[0] == '.'))) {
         put_s(chrom);
         adv((size_t)snprintf(w, (size_t)(end - w), "_%lld", (long long)pos));
     } else {
@@ -306,10 +379,18 @@ static size_t format_row_impl(char* buf, size_t cap, const char* chrom, int64_t 
     return (size_t)(w - buf);
 }
 
+namespace {
+size_t format_row_views(char* buf, size_t cap, const Site& s, float af, float miss_rate, const double* row, int out_cols) {
+    return format_row_impl(buf, cap, s.chrom, s.pos, s.snp, s.a0, s.a1, af, miss_rate, row, out_cols, true);
+}
+}  // namespace
+
+static Str cstr(const char* s) { Str t; t.p = s; t.n = (uint32_t)strlen(s); return t; }
+
 extern "C" size_t jxb_format_row(char* buf, size_t cap, const char* chrom, int64_t pos, const char* snp,
                                  const char* a0, const char* a1, float af, float miss_rate, const double* row,
                                  int out_cols) {
-    return format_row_impl(buf, cap, chrom, pos, snp, a0, a1, af, miss_rate, row, out_cols, true);
+    return format_row_impl(buf, cap, cstr(chrom), pos, cstr(snp), cstr(a0), cstr(a1), af, miss_rate, row, out_cols, true);
 }
 
 // transform_alleles_by_model, src/io/assoc2tsv.rs:117-137
@@ -332,11 +413,11 @@ extern "C" size_t jxb_format_block(char* buf, size_t cap, size_t rows, const cha
     std::vector<char> line;
     for (size_t r = 0; r < rows; ++r) {
         alleles_by_model(a0, a1, genetic_model, t0, t1);
-        const size_t need = format_row_need(chrom, snp, t0.c_str(), t1.c_str());
+        const size_t need = format_row_need(strlen(chrom), strlen(snp), t0.size(), t1.size());
         if (line.size() < need) line.resize(need);
         // write_chunk prints the caller's SNP names verbatim (no chrom_pos substitution)
-        const size_t len = format_row_impl(line.data(), line.size(), chrom, pos[r], snp, t0.c_str(), t1.c_str(), af[r],
-                                           miss_rate[r], res + r * (size_t)out_cols, out_cols, false);
+        const size_t len = format_row_impl(line.data(), line.size(), cstr(chrom), pos[r], cstr(snp), cstr(t0.c_str()), cstr(t1.c_str()),
+                                           af[r], miss_rate[r], res + r * (size_t)out_cols, out_cols, false);
         if (used + len <= cap) memcpy(buf + used, line.data(), len);
         used += len;
         chrom += strlen(chrom) + 1; snp += strlen(snp) + 1; a0 += strlen(a0) + 1; a1 += strlen(a1) + 1;
@@ -478,16 +559,20 @@ extern "C" int jxb_scan_bed_to_tsv(jxb_model* m, const jxb_bed_scan_cfg* cfg, si
     }
     const size_t span_max = prepared ? std::min(step, end - begin) : std::min(step, std::max<size_t>(total, 1));
     uint8_t* ring[kRing] = {nullptr, nullptr, nullptr};
+    size_t ring_cap[kRing] = {0, 0, 0};
     bool ring_free[kRing] = {true, true, true};
+    auto free_ring = [&]() { for (int k = 0; k < kRing; ++k) if (ring[k]) { pinned_pool().release(ring[k], ring_cap[k]); ring[k] = nullptr; } };
+    // a scan of fewer than kRing batches needs fewer slots
+    const size_t n_batches = (total + step - 1) / std::max<size_t>(step, 1);
     for (int k = 0; k < kRing; ++k) {
-        if (cudaHostAlloc((void**)&ring[k], std::max<size_t>(span_max * bps, 16), cudaHostAllocPortable) != cudaSuccess) {
-            (void)cudaGetLastError();
-            for (int j = 0; j < k; ++j) cudaFreeHost(ring[j]);
+        if ((size_t)k >= std::max<size_t>(n_batches, 1)) { ring_free[k] = false; continue; }
+        ring[k] = pinned_pool().acquire(std::max<size_t>(span_max * bps, 16), &ring_cap[k]);
+        if (!ring[k]) {
+            free_ring();
             wr.finish(); fclose(wr.fp); unmap();
             return fail(-36, "pinned staging ring: cudaHostAlloc of " + std::to_string(span_max * bps) + " bytes failed");
         }
     }
-    auto free_ring = [&]() { for (int k = 0; k < kRing; ++k) if (ring[k]) { cudaFreeHost(ring[k]); ring[k] = nullptr; } };
     size_t next_emit = cfg->progress_every ? std::max<size_t>(1, std::min(cfg->progress_every, total)) : 0;
     // Producer thread (the reference's producer, src/io/pipeline.rs:49-92): parses the BIM rows of the next batches and
     // builds their masks while the device scans the current one; errors travel with the item and are raised on the
@@ -584,7 +669,7 @@ extern "C" int jxb_scan_bed_to_tsv(jxb_model* m, const jxb_bed_scan_cfg* cfg, si
                 }
                 if (cfg->snps_only)
                     for (size_t r = 0; r < rows; ++r)
-                        if (!simple_snp_allele(b->sites[r].a0) || !simple_snp_allele(b->sites[r].a1)) it->mask[r] = 0;
+                        if (!simple_snp_allele(b->sites[r].a0.p, b->sites[r].a0.n) || !simple_snp_allele(b->sites[r].a1.p, b->sites[r].a1.n)) it->mask[r] = 0;
             }
             // packed rows of the batch: mmap (page cache / disk) -> a free pinned ring slot
             {

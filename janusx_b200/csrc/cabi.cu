@@ -179,6 +179,7 @@ int model_alloc(int device, size_t n, size_t p, bool with_ut, jxb_model** out) {
     rc |= dev_alloc(&m.fx_py, m.ldn);
     rc |= dev_alloc(&m.fx_wx, p * m.ldn);
     rc |= dev_alloc(&m.fx_scal, 8 + 32 * 32);
+    if (p <= 8) rc |= dev_alloc(&m.fx_rec, m.ldn * ((p + 2 + 1) / 2 * 2));
     if (with_ut) rc |= dev_alloc(&m.ut, m.n_pad * m.ldk);
     if (rc) { jxb_model_destroy(h); return rc; }
     *out = h;
@@ -615,6 +616,7 @@ void jxb_set_rotate_variant(int variant) { g_rotate_variant = variant; }
 void jxb_set_thread_solve_min_rows(size_t rows) { g_thread_solve_min_rows = rows; }
 void jxb_set_big_solve_kernel(int variant) { g_big_solve_kernel = variant == 1 ? 1 : 0; }
 void jxb_set_generic_divide(int on) { g_force_generic_divide = on ? 1 : 0; }
+void jxb_set_fixed_lane_min_rows(size_t rows) { g_fixed_lane_min_rows = rows; }
 
 int jxb_selftest_rcp(size_t count, int lo_exp, int hi_exp, uint64_t* mismatches) {
     if (!mismatches) return fail(-2, "null argument");
@@ -666,7 +668,7 @@ void jxb_model_destroy(jxb_model* h) {
     cudaSetDevice(m.device);
     if (m.stream) cudaStreamSynchronize(m.stream);
     void* ptrs[] = {m.s, m.y, m.xt, m.rec, m.ut, m.g64, m.rot, m.log_table, m.ssq, m.out, m.evals, m.packed, m.counts, m.af, m.src_row,
-                    m.n_kept, m.sample_idx, m.stage_f32, m.fx_w, m.fx_py, m.fx_wx, m.fx_scal, h->missr, h->mask,
+                    m.n_kept, m.sample_idx, m.stage_f32, m.fx_w, m.fx_py, m.fx_wx, m.fx_scal, m.fx_rec, h->missr, h->mask,
                     h->prep_af, h->prep_flip,
                     h->scal, m.q8, m.q8_inv_scale, m.q8_rk, m.a8, m.coef, m.flags8, m.c32, m.lt_ws, m.corr64};
     for (void* p : ptrs)
@@ -1097,6 +1099,46 @@ int jxb_decode_packed_prepared(jxb_model* h, const uint8_t* packed, size_t bps, 
         JXB_CUDA_OK(cudaMemcpyAsync(g_host, m.stage_f32, (size_t)nk * n * sizeof(float), cudaMemcpyDeviceToHost, m.stream));
         JXB_CUDA_OK(cudaStreamSynchronize(m.stream));
     }
+    return 0;
+}
+
+int jxb_decode_packed_meta(jxb_model* h, const uint8_t* packed, size_t bps, size_t rows, size_t n_full, const int64_t* sidx,
+                           const float* row_mean_host, float* g_host) {
+    if (!h || !packed || !row_mean_host || !g_host) return fail(-2, "null argument");
+    if (bps != (n_full + 3) / 4) return fail(-2, "bytes_per_snp must equal ceil(n_full/4)");
+    if (!sidx && n_full != h->m.n) return fail(-2, "sample_ids length != expected sample count");
+    if (rows == 0) return 0;
+    Model& m = h->m;
+    int rc = ensure_capacity(h, rows, bps, false);
+    if (rc) return rc;
+    const size_t n = m.n;
+    JXB_CUDA_OK(cudaMemcpyAsync(m.packed, packed, rows * bps, cudaMemcpyHostToDevice, m.stream));
+    const int64_t* sidx_dev = nullptr;
+    if (sidx) {
+        rc = ensure_sample_idx(m, sidx, n, false, n_full);
+        if (rc) return rc;
+        sidx_dev = m.sample_idx;
+    }
+    JXB_CUDA_OK(cudaMemcpyAsync(h->prep_af, row_mean_host, rows * sizeof(float), cudaMemcpyHostToDevice, m.stream));
+    rc = ensure_stage_f32(m, rows * n);
+    if (rc) return rc;
+    rc = launch_decode_center(m.packed, bps, nullptr, nullptr, rows, n_full, sidx_dev, n, m.af, m.counts, 0, nullptr, 0,
+                              m.stage_f32, n, m.stream, h->prep_af);
+    note_launch(1);
+    if (rc) return rc;
+    JXB_CUDA_OK(cudaMemcpyAsync(g_host, m.stage_f32, rows * n * sizeof(float), cudaMemcpyDeviceToHost, m.stream));
+    JXB_CUDA_OK(cudaStreamSynchronize(m.stream));
+    return 0;
+}
+
+int jxb_debug_fetch_rot(jxb_model* h, size_t row0, size_t rows, float* rot_host) {
+    if (!h || !rot_host) return fail(-2, "null argument");
+    Model& m = h->m;
+    if (!m.rot || row0 + rows > m.cap_rows) return fail(-2, "rows exceed the workspace");
+    JXB_CUDA_OK(cudaSetDevice(m.device));
+    JXB_CUDA_OK(cudaMemcpy2DAsync(rot_host, m.ldc * sizeof(float), m.rot + row0 * m.ldc, m.ldc * sizeof(float),
+                                  m.ldc * sizeof(float), rows, cudaMemcpyDeviceToHost, m.stream));
+    JXB_CUDA_OK(cudaStreamSynchronize(m.stream));
     return 0;
 }
 

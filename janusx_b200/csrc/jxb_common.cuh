@@ -80,6 +80,7 @@ struct Model {
     double* ssq = nullptr; size_t ssq_cap = 0;           // per-row sum of squares (lane-per-SNP solve)
     // fixed-lambda cache (A14)
     float* fx_w = nullptr; float* fx_py = nullptr; float* fx_wx = nullptr; double* fx_scal = nullptr;
+    double* fx_rec = nullptr;                            // [ldn][round_up(p+2,2)] interleaved f64 records (p <= 8)
     double fx_log10_lbd = 0.0; bool fx_valid = false;
 };
 
@@ -99,7 +100,8 @@ int launch_compact(const int32_t* counts, size_t rows, int32_t* src_row, int32_t
 int launch_decode_center(const uint8_t* packed, size_t bps, const int32_t* src_row, const int32_t* n_kept,
                          size_t max_rows, size_t n_full, const int64_t* sample_idx, size_t n,
                          const float* af_by_src, const int32_t* counts_by_src, int model_code,
-                         double* g64, size_t ldk, float* g32, size_t ld32, cudaStream_t st);
+                         double* g64, size_t ldk, float* g32, size_t ld32, cudaStream_t st,
+                         const float* meta_mean = nullptr /* by source row: decode with LUT [0-mean, 0, 1-mean, 2-mean], no centring */);
 int launch_widen_f32(const float* src, size_t ld_src, size_t rows, size_t n, double* dst, size_t ldk,
                      cudaStream_t st);
 // out: transposed ? rotT-style [n][ld] : row-major [rows][ld]
@@ -116,6 +118,7 @@ int launch_solve_lane(Model& m, const float* rot, size_t ldc, size_t max_rows, c
                       const SolveParams& sp, double* out, int out_cols, int32_t* evals, int32_t* queue, cudaStream_t st);
 int rcp_selftest(size_t count, int lo_exp, int hi_exp, unsigned long long* mismatches_host);
 extern int g_force_generic_divide;
+extern size_t g_fixed_lane_min_rows;
 // streamed scan: solve while later row slabs are still being rotated (k3_solve.cu / cabi.cu scan_streamed)
 int ensure_solve_lane_buffers(Model& m, size_t max_rows, cudaStream_t st);
 int launch_row_ssq_publish(Model& m, const float* rot, size_t ldc, size_t row0, size_t row1, int32_t* sync, cudaStream_t st);

@@ -58,7 +58,7 @@ int JXB_CAT(k3_launch_solve_lane_p, JXB_P)(const k3::ModelView& mv, int sms, con
                                            const int32_t* n_rows_dev, const SolveParams& sp, double* out, int out_cols,
                                            int32_t* evals, const void* log_table, double* ssq, int32_t* queue,
                                            int fast_rcp, cudaStream_t st) {
-    constexpr int kSmem = 4 * (int)sizeof(k3::ThreadTile<JXB_P>);
+    constexpr int kSmem = 4 * (int)sizeof(k3::ThreadTile<JXB_P, JXB_K3L_TILE>);
     constexpr int kPerSm = (JXB_P <= 4) ? JXB_K3T_MINB : 3;
     static bool attr = false;
     if (!attr) {
@@ -104,6 +104,22 @@ int JXB_CAT(k3_solve_lane_stream_res_p, JXB_P)(int* regs, int* smem) {
     if (cudaFuncGetAttributes(&fa, k3::solve_lane_stream_kernel<JXB_P>) != cudaSuccess) return -1;
     *regs = fa.numRegs;
     *smem = (int)fa.sharedSizeBytes + 4 * (int)sizeof(k3::ThreadTile<JXB_P, 16>);
+    return 0;
+}
+
+// fixed-lambda scan of large batches: lane per SNP (frec = interleaved f64 records written by fixed_prepare_kernel)
+int JXB_CAT(k3_launch_fixed_lane_p, JXB_P)(const k3::ModelView& mv, int sms, const double* frec, const double* scal,
+                                           const float* rot, size_t ldc, int max_rows, const int32_t* n_rows_dev,
+                                           int has_nullml, double nullml, double* out, int out_cols, cudaStream_t st) {
+    constexpr int kSmem = 4 * (int)sizeof(k3::FixedTile<JXB_P>);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k3::fixed_lane_kernel<JXB_P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+        attr = true;
+    }
+    const int blocks = std::max(1, std::min((max_rows + 127) / 128, sms * 4));
+    k3::fixed_lane_kernel<JXB_P><<<blocks, 128, kSmem, st>>>(mv, frec, scal, rot, ldc, max_rows, n_rows_dev, has_nullml, nullml,
+                                                            out, out_cols);
     return 0;
 }
 

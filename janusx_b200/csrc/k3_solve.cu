@@ -19,10 +19,13 @@ namespace jxb {
                                   int, cudaStream_t);                                                          \
     int k3_launch_solve_lane_stream_p##P(const k3::ModelView&, int, const float*, size_t, int, const SolveParams&, \
                                          double*, int, int32_t*, const void*, const double*, int32_t*, cudaStream_t); \
-    int k3_solve_lane_stream_res_p##P(int*, int*);
+    int k3_solve_lane_stream_res_p##P(int*, int*);                                                             \
+    int k3_launch_fixed_lane_p##P(const k3::ModelView&, int, const double*, const double*, const float*, size_t, int, \
+                                  const int32_t*, int, double, double*, int, cudaStream_t);
 JXB_DECL_P(1) JXB_DECL_P(2) JXB_DECL_P(3) JXB_DECL_P(4) JXB_DECL_P(5) JXB_DECL_P(6) JXB_DECL_P(7) JXB_DECL_P(8)
 #undef JXB_DECL_P
 
+size_t g_fixed_lane_min_rows = 4096;   // fixed-lambda batches at least this large use the lane-per-SNP kernel
 int g_force_generic_divide = 0;   // tests: compare the rcp_fast kernels with the compiler-divide kernels
 
 namespace {
@@ -245,7 +248,9 @@ int launch_fixed_prepare(Model& m, double log10_lbd, cudaStream_t st) {
     if (m.p < 1 || m.p > (size_t)kDynMaxCov) return fail(-2, "covariate columns must be in [1, 32]");
     const ModelView mv = view_of(m);
     const double lbd = pow(10.0, log10_lbd);
-    fixed_prepare_kernel<<<1, 32, 0, st>>>(mv, lbd, m.fx_w, m.fx_py, m.fx_wx, m.fx_scal);
+    const int frs = (int)((m.p + 2 + 1) / 2 * 2);
+    if (m.fx_rec) JXB_CUDA_OK(cudaMemsetAsync(m.fx_rec, 0, m.ldn * frs * sizeof(double), st));
+    fixed_prepare_kernel<<<1, 32, 0, st>>>(mv, lbd, m.fx_w, m.fx_py, m.fx_wx, m.fx_scal, m.fx_rec, frs);
     JXB_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -255,6 +260,17 @@ int launch_fixed_solve(const Model& m, const float* rot, size_t ldc, size_t max_
     if (max_rows == 0) return 0;
     if (m.p > 30) return fail(-2, "fixed-lambda scan supports at most 30 covariate columns");
     const ModelView mv = view_of(m);
+    if (m.p <= 8 && m.fx_rec && max_rows >= g_fixed_lane_min_rows) {
+        // large batches: lane per SNP, one HBM-bound pass over the rotated block (same ordered sums)
+        const int sms = sm_count(m.device);
+#define F_STATIC(P) k3_launch_fixed_lane_p##P(mv, sms, m.fx_rec, m.fx_scal, rot, ldc, (int)max_rows, n_rows_dev, has_nullml, nullml, out, out_cols, st)
+#define F_DYN() (void)0
+        JXB_DISPATCH_P((int)m.p, F_STATIC, F_DYN)
+#undef F_STATIC
+#undef F_DYN
+        JXB_CUDA_OK(cudaGetLastError());
+        return 0;
+    }
     const int smem = 8 * 32 * 33 * (int)sizeof(double);
     static bool attr = false;
     if (!attr) {

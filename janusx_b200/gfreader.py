@@ -330,3 +330,70 @@ def prepare_bed_logic_keep_mask(prefix, sample_indices=None, maf_threshold=0.0, 
     out = prepare_bed_logic_meta_selected(prefix, sample_indices, maf_threshold, max_missing_rate, het_threshold, snps_only,
                                           mmap_window_mb, threads, device)
     return out[4], out[5], out[6]
+
+
+class BedChunkReaderFromMeta(BedChunkReader):
+    """src/io/gfreader.rs:7440-7730: the chunk source of the "meta-shared" route -- several models scan one trait with
+    ONE prepared row list (prepare_bed_logic_meta_selected) instead of re-deriving QC per model
+    (workflow_model_stream.py:400-415).  Rows are decoded with the shared metadata: mean = 2 * ALT frequency
+    (row_maf, flipped to 1 - maf where row_flip), missing calls -> 0, no re-centring; af = mean / 2 and the caller's
+    row_missing are returned per row.  Additive coding only, like the reference."""
+
+    def __init__(self, prefix, row_indices, row_flip, row_missing, row_maf, sample_ids=None, sample_indices=None,
+                 mmap_window_mb=None, device: int = 0):
+        super().__init__(prefix, sample_ids=sample_ids, sample_indices=sample_indices, device=device)
+        idx = np.ascontiguousarray(np.asarray(row_indices, dtype=np.int64).reshape(-1))
+        flip = np.asarray(row_flip, dtype=bool).reshape(-1)
+        miss = np.ascontiguousarray(np.asarray(row_missing, dtype=np.float32).reshape(-1))
+        maf = np.asarray(row_maf, dtype=np.float32).reshape(-1)
+        m = idx.shape[0]
+        if flip.shape[0] != m or miss.shape[0] != m or maf.shape[0] != m:
+            raise ValueError(f"metadata length mismatch: row_indices={m}, row_flip={flip.shape[0]}, "
+                             f"row_missing={miss.shape[0]}, row_maf={maf.shape[0]}")
+        n_total = len(self._sites)
+        if m and (idx.min() < 0 or idx.max() >= n_total):
+            bad = int(idx[(idx < 0) | (idx >= n_total)][0])
+            raise ValueError(f"row index out of range: {bad} for n_snps={n_total}")
+        if m > 1 and np.any(np.diff(idx) < 0):
+            raise ValueError("row_indices must be sorted in ascending BED order")
+        self._rows = idx
+        self._row_missing = miss
+        # gfreader.rs:7541-7550: alt mean = 2 * clamp(flip ? 1 - clamp(maf) : clamp(maf)) in f32
+        mc = np.clip(maf, np.float32(0.0), np.float32(1.0)).astype(np.float32)
+        alt = np.where(flip, np.float32(1.0) - mc, mc).astype(np.float32)
+        self._row_alt_mean = (np.float32(2.0) * np.clip(alt, np.float32(0.0), np.float32(1.0))).astype(np.float32)
+        self._pos = 0
+
+    @property
+    def n_snps(self) -> int:
+        return int(self._rows.shape[0])
+
+    def next_chunk(self, *_a, **_k):
+        raise NotImplementedError("BedChunkReaderFromMeta only serves next_chunk_prepared (like the reference)")
+
+    def next_chunk_prepared(self, chunk_size, coding=None, snps_only=False):
+        if int(chunk_size) <= 0:
+            raise ValueError("chunk_size must be > 0")
+        if (coding or "add").strip().lower() != "add":
+            raise ValueError("BedChunkReaderFromMeta currently supports additive coding only")
+        if self.n_samples == 0:
+            return None
+        meta_idx = []
+        while len(meta_idx) < int(chunk_size) and self._pos < self._rows.shape[0]:
+            k = self._pos
+            self._pos += 1
+            site = self._sites[int(self._rows[k])]
+            if snps_only and not (_simple_allele(site.ref_allele) and _simple_allele(site.alt_allele)):
+                continue
+            meta_idx.append(k)
+        if not meta_idx:
+            return None
+        meta_idx = np.asarray(meta_idx, dtype=np.int64)
+        src = self._rows[meta_idx]
+        packed = np.ascontiguousarray(self._packed[src])
+        mean = np.ascontiguousarray(self._row_alt_mean[meta_idx])
+        g = np.empty((src.shape[0], self.n_samples), dtype=np.float32)
+        check(lib().jxb_decode_packed_meta(self._dev.handle, ptr(packed), packed.shape[1], packed.shape[0], self._n_full,
+                                           None if self._identity else ptr(self._sidx), ptr(mean), ptr(g)))
+        sites = [self._sites[int(j)] for j in src]
+        return g, sites, (mean * np.float32(0.5)).astype(np.float32), np.ascontiguousarray(self._row_missing[meta_idx])

@@ -28,6 +28,14 @@ import sys
 import time
 from typing import List, Optional
 
+# The eigensolver (cusolverDnXsyevd) has a host stage whose summation order follows the host thread count, and
+# torchrun exports OMP_NUM_THREADS=1 to its ranks: the same GRM would decompose to different last bits under
+# `-gpus 1` and `-gpus 8`.  The rank that decomposes (rank 0) therefore always runs with the cores of its affinity
+# mask, set before any threaded library is loaded, so every launch mode on one box yields the same null model and
+# with it a byte-identical TSV.
+if int(os.environ.get("RANK", "0")) == 0:
+    os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+
 import numpy as np
 
 
@@ -263,6 +271,9 @@ def main(argv: Optional[List[str]] = None) -> int:
                 _, nullml = base.device_model.ml_null(float(base.bounds[0]), float(base.bounds[1]), 30, 1e-2, l10)
             nm = D.NullModel(s=base.S, xcov=base.Xcov, y=base.y[:, 0].copy(), u_t=base.Dh, low=float(base.bounds[0]),
                              high=float(base.bounds[1]), lbd_null=float(base.lbd_null), nullml=nullml)
+            if os.environ.get("JXB_DEBUG_DUMP_NULL"):      # development aid: the null model this run scanned with
+                np.savez(os.environ["JXB_DEBUG_DUMP_NULL"], s=nm.s, xcov=nm.xcov, y=nm.y, u_t=nm.u_t, low=nm.low, high=nm.high,
+                         lbd=nm.lbd_null, nullml=nm.nullml, K=K)
         if world > 1:
             flag = [go]
             dist.broadcast_object_list(flag, src=0)

@@ -1211,7 +1211,7 @@ def gwas_lmm_lm_null_lrt_decision(y, x_cov, lmm_ml0, alpha=0.05, boundary_mixtur
 
 def __getattr__(name):
     # `janusx.janusx.BedChunkReader` lives in gfreader.py (which imports this module): resolve it lazily
-    if name in ("BedChunkReader", "prepare_bed_logic_meta_selected", "prepare_bed_logic_keep_mask"):
+    if name in ("BedChunkReader", "BedChunkReaderFromMeta", "prepare_bed_logic_meta_selected", "prepare_bed_logic_keep_mask"):
         from . import gfreader
         return getattr(gfreader, name)
     raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

@@ -744,6 +744,14 @@ def test_full_batch_at_full_size_sampled_parity(jx, oracle, n, model):
         want_f, _ = oracle.lmm_assoc_chunk_f32(s_np, xo, yo[:, 0], l10, rot_o, 0, None)
         assert_results_close(out_f[pos[picks]], want_f)
         assert np.isfinite(out_f[:, :2]).all()
+        # the lane-per-SNP fixed-lambda kernel (large batches) against the warp-per-SNP one: same ordered sums, same bits
+        jx._cabi.lib().jxb_set_fixed_lane_min_rows(1 << 40)
+        try:
+            mdl.scan_packed_dev(pk.data_ptr(), rows, bps, n, None, mode="fvlmm", log10_lbd=l10)
+            _, _, _, out_w, _ = mdl.scan_fetch(rows, cols_f)
+        finally:
+            jx._cabi.lib().jxb_set_fixed_lane_min_rows(4096)
+        assert np.array_equal(out_f, out_w, equal_nan=True)
 
 
 def test_config2_bed_to_tsv_n5000(jx, oracle, tmp_path):

@@ -148,3 +148,40 @@ def test_prepared_row_statistics_feed_the_bed_scan(jx, oracle, tmp_path):
     assert np.array_equal(r2[4], k2) and np.array_equal(r2[2].view(np.uint32), af2[k2].view(np.uint32))
     with pytest.raises(ValueError, match="sample index out of range"):
         jx.prepare_bed_logic_meta_selected(prefix, np.array([0, case.n]))
+
+
+def test_bed_chunk_reader_from_meta(jx, oracle, tmp_path):
+    """BedChunkReaderFromMeta (src/io/gfreader.rs:7440-7730): rows listed by the shared per-trait metadata, decoded as
+    (code - 2*af) with missing -> 0 and no re-centring; chunking and snps_only follow the row list."""
+    from janusx_b200 import synth
+    case = make_problem(n=150, m=300, q=0, seed=12, missing_rate=0.05)
+    prefix = str(tmp_path / "p")
+    synth.write_plink(prefix, case.packed, case.n)
+    sub = np.arange(3, case.n, 2, dtype=np.int64)
+    row_idx, miss, af, flip, _, _, _ = jx.prepare_bed_logic_meta_selected(prefix, sub, 0.05, 0.2, 1.0)
+    flip = flip.copy()
+    flip[::7] = True                                   # exercised although the reference's own metadata never sets it
+    rd = jx.BedChunkReaderFromMeta(prefix, row_idx, flip, miss, af, sample_indices=sub)
+    assert rd.n_snps == row_idx.size and rd.n_samples == sub.size
+    gs, afs, ms, names = [], [], [], []
+    while True:
+        out = rd.next_chunk_prepared(64)
+        if out is None:
+            break
+        g, sites, a, mi = out
+        gs.append(g); afs.append(a); ms.append(mi); names += [s.snp for s in sites]
+    g = np.concatenate(gs)
+    assert g.shape == (row_idx.size, sub.size) and names == [f"snp{i}" for i in row_idx]
+    # row-by-row restatement
+    mc = np.clip(af, 0, 1).astype(np.float32)
+    alt_mean = (np.float32(2.0) * np.where(flip, np.float32(1.0) - mc, mc)).astype(np.float32)
+    codes = np.stack([(case.packed[:, sub // 4] >> ((sub % 4) * 2)) & 3])[0][row_idx]       # [rows, samples]
+    lut = np.stack([np.float32(0.0) - alt_mean, np.zeros_like(alt_mean), np.float32(1.0) - alt_mean,
+                    np.float32(2.0) - alt_mean], axis=1)
+    want = np.take_along_axis(lut, codes.astype(np.int64), axis=1)
+    assert np.array_equal(g.view(np.uint32), want.view(np.uint32))
+    assert np.array_equal(np.concatenate(afs), alt_mean * np.float32(0.5)) and np.array_equal(np.concatenate(ms), miss)
+    with pytest.raises(ValueError, match="sorted in ascending BED order"):
+        jx.BedChunkReaderFromMeta(prefix, row_idx[::-1], flip, miss, af)
+    with pytest.raises(ValueError, match="additive coding only"):
+        jx.BedChunkReaderFromMeta(prefix, row_idx, flip, miss, af, sample_indices=sub).next_chunk_prepared(8, coding="dom")

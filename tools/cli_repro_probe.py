@@ -15,8 +15,10 @@ from conftest import make_problem  # noqa: E402
 from janusx_b200 import synth  # noqa: E402
 
 
-def run(args):
+def run(args, dump=None):
     env = dict(os.environ, PYTHONPATH=str(ROOT))
+    if dump:
+        env["JXB_DEBUG_DUMP_NULL"] = dump
     r = subprocess.run([sys.executable, "-m", "janusx_b200.gwas", *args], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
                        text=True)
     if r.returncode:
@@ -38,10 +40,12 @@ def main():
     for tag, g in (("a1", 1), ("b1", 1), ("c2", 2)):
         out = tmp / tag
         log = run(["-bfile", prefix, "-p", str(tmp / "pheno.tsv"), "-lmm", "-k", "1", "-q", "2", "-force-model", "-gpus", str(g),
-                   "-o", str(out), "-prefix", "run"])
+                   "-o", str(out), "-prefix", "run"], dump=str(tmp / f"null_{tag}.npz"))
         print(tag, [l for l in log.splitlines() if "lambda_null" in l])
         outs[tag] = (out / "run.traitA.lmm.tsv").read_text().splitlines()
     for x, y in (("a1", "b1"), ("a1", "c2")):
+        za, zb = np.load(tmp / f"null_{x}.npz"), np.load(tmp / f"null_{y}.npz")
+        print(x, y, "null model:", {k: (bool(np.array_equal(za[k], zb[k])), float(np.max(np.abs(za[k] - zb[k])))) for k in za.files})
         a, b = outs[x], outs[y]
         diff = [i for i, (p, q) in enumerate(zip(a, b)) if p != q]
         print(x, y, "lines", len(a), len(b), "differing", len(diff))
