@@ -125,10 +125,34 @@ SYMBOLS = {
 }
 
 
+def _preload_cuda_math_libs() -> None:
+    """libjxb200.so opens cuSOLVER / cuBLASLt by soname at first use.  A process that imported torch already holds the
+    copies bundled with the `nvidia-*` wheels, one that did not would pick the toolkit's (another version): the same GRM
+    then decomposes to different last bits depending on whether torch happens to be loaded (seen: `-gpus 1` vs `-gpus 2`).
+    Load the bundled copies first, when they exist, so every process resolves the same libraries."""
+    import importlib.util
+    try:
+        spec = importlib.util.find_spec("nvidia")
+    except (ImportError, ValueError):
+        spec = None
+    roots = list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []
+    for rel in ("cuda_runtime/lib/libcudart.so.12", "nvjitlink/lib/libnvJitLink.so.12", "cublas/lib/libcublasLt.so.12",
+                "cublas/lib/libcublas.so.12", "cusparse/lib/libcusparse.so.12", "cusolver/lib/libcusolver.so.11"):
+        for root in roots:
+            path = Path(root) / rel
+            if path.exists():
+                try:
+                    C.CDLL(str(path), mode=C.RTLD_GLOBAL)
+                except OSError:
+                    pass
+                break
+
+
 def lib() -> C.CDLL:
     """Load libjxb200.so (built in-tree by janusx_b200/build.py).  No fallback of any kind."""
     global _lib
     if _lib is None:
+        _preload_cuda_math_libs()
         if not LIB_PATH.exists():
             raise JxbError(
                 f"{LIB_PATH} is missing: build it with `python -m janusx_b200.build` "

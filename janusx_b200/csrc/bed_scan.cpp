@@ -20,6 +20,7 @@
 
 #include <algorithm>
 #include <cerrno>
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <cstdio>
@@ -562,8 +563,10 @@ extern "C" int jxb_scan_bed_to_tsv(jxb_model* m, const jxb_bed_scan_cfg* cfg, si
     size_t ring_cap[kRing] = {0, 0, 0};
     bool ring_free[kRing] = {true, true, true};
     auto free_ring = [&]() { for (int k = 0; k < kRing; ++k) if (ring[k]) { pinned_pool().release(ring[k], ring_cap[k]); ring[k] = nullptr; } };
-    // a scan of fewer than kRing batches needs fewer slots
-    const size_t n_batches = (total + step - 1) / std::max<size_t>(step, 1);
+    // a scan of fewer than kRing batches needs fewer slots.  Upper bound on the batch count: batches are BED-row spans of
+    // at most `step` rows (prepared lists may leave most rows of a span unlisted, so the listed count says nothing)
+    const size_t span_rows = prepared ? (end > begin ? end - begin : 0) : total;
+    const size_t n_batches = (span_rows + step - 1) / std::max<size_t>(step, 1);
     for (int k = 0; k < kRing; ++k) {
         if ((size_t)k >= std::max<size_t>(n_batches, 1)) { ring_free[k] = false; continue; }
         ring[k] = pinned_pool().acquire(std::max<size_t>(span_max * bps, 16), &ring_cap[k]);
@@ -696,7 +699,14 @@ extern "C" int jxb_scan_bed_to_tsv(jxb_model* m, const jxb_bed_scan_cfg* cfg, si
 
     int rc = 0;
     size_t scanned = 0;
+    // JXB_BED_TIMING=1: where the calling thread's wall time goes (waiting for the producer, staging, device scan,
+    // handing rows to the writer), printed to stderr at the end
+    const bool timing = getenv("JXB_BED_TIMING") != nullptr;
+    double t_pop = 0, t_stage = 0, t_scan = 0, t_push = 0;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
     auto pop = [&]() {
+        const double t0 = now();
         Prep* it = nullptr;
         std::unique_lock<std::mutex> lk(pmu);
         pcv.wait(lk, [&] { return !pq.empty(); });
@@ -704,6 +714,7 @@ extern "C" int jxb_scan_bed_to_tsv(jxb_model* m, const jxb_bed_scan_cfg* cfg, si
         pq.pop_front();
         lk.unlock();
         pcv.notify_all();
+        t_pop += now() - t0;
         return it;
     };
     auto release_slot = [&](Prep* it) {
@@ -723,8 +734,11 @@ extern "C" int jxb_scan_bed_to_tsv(jxb_model* m, const jxb_bed_scan_cfg* cfg, si
         // jxb_scan_staged waits for cur's copy and makes it the working buffer; nxt is staged right after the swap is
         // ordered, i.e. from inside the same call sequence: stage it first into the OTHER buffer -- the library keeps
         // two device buffers and swaps them at every scan
+        double t0 = now();
         rc = jxb_scan_staged_begin(m);
         if (!rc && !nxt->last) rc = jxb_stage_packed(m, ring[nxt->slot], bps, nxt->rows);
+        t_stage += now() - t0;
+        t0 = now();
         if (!rc)
             rc = jxb_scan_staged(m, n_full, identity ? nullptr : sidx.data(), cur->has_mask ? cur->mask.data() : nullptr,
                                  cur->row_af.empty() ? nullptr : cur->row_af.data(),
@@ -734,7 +748,10 @@ extern "C" int jxb_scan_bed_to_tsv(jxb_model* m, const jxb_bed_scan_cfg* cfg, si
         if (!cur->row_miss.empty())
             for (size_t r = 0; r < cur->rows; ++r)
                 if (cur->row_miss[r] >= 0) b->missing[r] = cur->row_miss[r];
+        t_scan += now() - t0;
+        t0 = now();
         wr.push(b);
+        t_push += now() - t0;
         cur->b = nullptr;
         scanned += prepared ? cur->listed : cur->rows;
         drop(cur);
@@ -758,7 +775,11 @@ extern "C" int jxb_scan_bed_to_tsv(jxb_model* m, const jxb_bed_scan_cfg* cfg, si
     pq.clear();
     free_ring();
     if (rc == 0 && cb) cb(total, total, user);
+    const double t_loop = now();
     wr.finish();
+    if (timing)
+        fprintf(stderr, "[jxb bed scan] batches of %zu rows: wait-producer %.3f s, stage %.3f s, device scan %.3f s, push %.3f s, "
+                        "loop %.3f s, writer drain %.3f s\n", step, t_pop, t_stage, t_scan, t_push, t_loop - t_begin, now() - t_loop);
     const bool ioerr = wr.io_error || fclose(wr.fp) != 0;
     unmap();
     if (rc) return rc;
