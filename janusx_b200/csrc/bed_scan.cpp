@@ -635,6 +635,15 @@ extern "C" int jxb_scan_bed_to_tsv(jxb_model* m, const jxb_bed_scan_cfg* cfg, si
             b->missing.resize(rows);
             b->out.resize(rows * out_cols);
             b->out_cols = out_cols;
+            // packed rows of the batch: mmap (page cache / disk) -> a free pinned ring slot, copied by a helper thread
+            // while this thread parses the batch's BIM rows
+            {
+                std::unique_lock<std::mutex> lk(pmu);
+                pcv.wait(lk, [&] { return stop || ring_free[0] || ring_free[1] || ring_free[2]; });
+                if (stop) { delete b; delete it; return; }
+                for (int k = 0; k < kRing; ++k) if (ring_free[k]) { it->slot = k; ring_free[k] = false; break; }
+            }
+            std::thread copier([&, c0, rows] { memcpy(ring[it->slot], payload + c0 * bps, rows * bps); });
             // BIM is read sequentially: skip the lines between the previous batch and this one
             int bad = 0;
             size_t need = c0;
@@ -643,7 +652,9 @@ extern "C" int jxb_scan_bed_to_tsv(jxb_model* m, const jxb_bed_scan_cfg* cfg, si
                 need = c0 + rows;
                 for (size_t r = 0; r < rows && !bad; ++r) bad = bim.next(b->sites[r], perr);
             }
+            copier.join();
             if (bad) {
+                { std::lock_guard<std::mutex> lk(pmu); ring_free[it->slot] = true; }
                 delete b; delete it;
                 bail(-29, bad < 0 ? perr : "BIM ended early: needed row " + std::to_string(need) + " but only saw " +
                                              std::to_string(bim.next_row) + " rows from " + bim.path);
@@ -674,14 +685,6 @@ extern "C" int jxb_scan_bed_to_tsv(jxb_model* m, const jxb_bed_scan_cfg* cfg, si
                     for (size_t r = 0; r < rows; ++r)
                         if (!simple_snp_allele(b->sites[r].a0.p, b->sites[r].a0.n) || !simple_snp_allele(b->sites[r].a1.p, b->sites[r].a1.n)) it->mask[r] = 0;
             }
-            // packed rows of the batch: mmap (page cache / disk) -> a free pinned ring slot
-            {
-                std::unique_lock<std::mutex> lk(pmu);
-                pcv.wait(lk, [&] { return stop || ring_free[0] || ring_free[1] || ring_free[2]; });
-                if (stop) { delete b; delete it; return; }
-                for (int k = 0; k < kRing; ++k) if (ring_free[k]) { it->slot = k; ring_free[k] = false; break; }
-            }
-            memcpy(ring[it->slot], payload + c0 * bps, rows * bps);
             if (!emit(it)) return;
             c0 += rows;
         }

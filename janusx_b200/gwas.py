@@ -273,7 +273,7 @@ def main(argv: Optional[List[str]] = None) -> int:
                              high=float(base.bounds[1]), lbd_null=float(base.lbd_null), nullml=nullml)
             if os.environ.get("JXB_DEBUG_DUMP_NULL"):      # development aid: the null model this run scanned with
                 np.savez(os.environ["JXB_DEBUG_DUMP_NULL"], s=nm.s, xcov=nm.xcov, y=nm.y, u_t=nm.u_t, low=nm.low, high=nm.high,
-                         lbd=nm.lbd_null, nullml=nm.nullml, K=K)
+                         lbd=nm.lbd_null, nullml=nm.nullml, **({"K": K} if n <= 5000 else {}))
         if world > 1:
             flag = [go]
             dist.broadcast_object_list(flag, src=0)
