@@ -277,6 +277,10 @@ size_t jxb_format_block(char* buf, size_t cap, size_t rows, const char* chrom, c
                         const char* a0, const char* a1, const float* af, const float* miss_rate, const double* res,
                         int out_cols, int genetic_model);
 
+/* Position-dependent checksum of a host buffer, computed at memory bandwidth on up to 8 threads (cache key of the
+ * resident U^T in the Python front end). */
+void jxb_host_checksum(const void* data, size_t bytes, uint64_t out2[2]);
+
 /* Header line for 3 / 4 / 6 result columns (AssocResultCols::header, src/io/assoc2tsv.rs:45-57); NULL otherwise. */
 const char* jxb_tsv_header(int out_cols);
 

@@ -391,6 +391,22 @@ def _digest(a: np.ndarray, sample: int = 1 << 16) -> bytes:
     return hashlib.blake2b(np.ascontiguousarray(flat).tobytes(), digest_size=12).digest()
 
 
+def _ut_key(ut: np.ndarray):
+    """Cache key of a U^T argument: shape, dtype and a position-dependent checksum over EVERY entry (one threaded pass at
+    memory bandwidth in libjxb200, ~30 ms for the 1.6 GB of n = 20,000), recomputed on every call -- so a matrix that
+    differs anywhere from the resident one, including one modified in place, is never mistaken for it."""
+    c = np.ascontiguousarray(ut)
+    out = (C.c_uint64 * 2)()
+    lib().jxb_host_checksum(c.ctypes.data, c.nbytes, out)
+    return (ut.shape, str(ut.dtype), int(out[0]), int(out[1]))
+
+
+def _evict_over_capacity() -> None:
+    while len(_CACHE) > _CACHE_MAX:
+        _, old = _CACHE.popitem(last=False)
+        old.close()
+
+
 def _get_model(s, xcov, y_rot, u_t=None) -> DeviceModel:
     s = _f64(s).reshape(-1)
     xcov = _f64(xcov)
@@ -405,7 +421,7 @@ def _get_model(s, xcov, y_rot, u_t=None) -> DeviceModel:
         ut = np.asarray(u_t)
         if ut.ndim != 2 or ut.shape != (n, n):
             raise RuntimeError("u_t must be (n, n) and row-major U^T")
-    ut_key = None if ut is None else (ut.shape, str(ut.dtype), _digest(ut))
+    ut_key = None if ut is None else _ut_key(ut)
     key_small = (n, xcov.shape[1], _digest(s, 1 << 30), _digest(xcov, 1 << 30), _digest(y, 1 << 30))
     for key, mdl in list(_CACHE.items()):
         if key[0] == key_small and (ut_key is None or key[1] == ut_key):
@@ -419,11 +435,15 @@ def _get_model(s, xcov, y_rot, u_t=None) -> DeviceModel:
                 mdl.set_xy(xcov, y)
                 _CACHE[(key_small, ut_key)] = mdl
                 return mdl
+        # a rotate-only placeholder (lmm_rotate_x_y_with_ut_f64) holding the same U^T: release it first so the matrix
+        # and its digit planes are never resident twice (~37 GB each at n = 50,000)
+        for key, mdl in list(_CACHE.items()):
+            if key[1] == ut_key and key[0][2:4] == (b"rot", b"rot"):
+                del _CACHE[key]
+                mdl.close()
     mdl = DeviceModel(s, xcov, y, ut)
     _CACHE[(key_small, ut_key)] = mdl
-    while len(_CACHE) > _CACHE_MAX:
-        _, old = _CACHE.popitem(last=False)
-        old.close()
+    _evict_over_capacity()
     return mdl
 
 
@@ -521,7 +541,7 @@ def lmm_rotate_x_y_with_ut_f64(u_t, x, y, threads=0):
     if ut.shape != (n, n):
         raise RuntimeError("u_t must be shape (n, n) and row-major U^T")
     # the model only needs U^T here; S / Xcov / y are placeholders of the right shape
-    ut_key = (ut.shape, str(ut.dtype), _digest(ut))
+    ut_key = _ut_key(ut)
     for key, mdl in _CACHE.items():
         if key[1] == ut_key:
             return mdl.rotate_xy(x, y)
