@@ -138,7 +138,9 @@ def scan_bed_sharded(bed_prefix: str, out_tsv: str, n_snps: int, scan_range: Cal
     use_cuda = dist.get_backend() == "nccl"
     dev = torch.device(f"cuda:{torch.cuda.current_device()}") if use_cuda else torch.device("cpu")
     tot = torch.tensor([rows], dtype=torch.int64, device=dev)
-    dist.all_reduce(tot)             # doubles as the completion barrier
+    dist.all_reduce(tot)             # doubles as the completion barrier ...
+    total = int(tot.item())          # ... once the HOST has seen its result: an NCCL collective returns as soon as it is
+                                     # enqueued, and rank 0 must not read a part file another rank is still writing
     if rank == 0:
         with open(out_tsv, "wb") as out:
             for r in range(world):
@@ -148,4 +150,4 @@ def scan_bed_sharded(bed_prefix: str, out_tsv: str, n_snps: int, scan_range: Cal
                 os.remove(p)
     if barrier:
         dist.barrier()
-    return int(tot.item())
+    return total

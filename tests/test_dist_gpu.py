@@ -107,6 +107,7 @@ def test_cli_one_job_on_n_ranks_is_byte_identical(tmp_path, oracle):
         assert not list(out.glob("*.part*")) and not list(out.glob("*.tmp")), log
     for g in counts[1:]:
         for m in ("lmm", "lmm2", "fvlmm"):
+            assert outs[g][m].count(b"\n") == outs[1][m].count(b"\n"), (g, m, "row count")
             assert outs[g][m] == outs[1][m], (g, m)
     # every kept SNP exactly once, in BED order
     keep, af, mr, missing = oracle.count_qc_block(case.packed, case.n, None, 0.02, 0.05, 1.0)
