@@ -174,11 +174,13 @@ int jxb_decode_packed_prepared(jxb_model* m, const uint8_t* packed_host, size_t 
                                const int64_t* sample_idx_host, const uint8_t* keep_host, const float* af_host,
                                int genetic_model, float* g_host, size_t* n_kept);
 
-/* Decode with caller-supplied row means and NO centring: BedChunkReaderFromMeta.next_chunk_prepared
- * (src/io/gfreader.rs:7623-7730): value LUT [(0 - mean), 0 (missing), (1 - mean), (2 - mean)] in f32, mean = 2 * ALT
- * frequency from the shared per-trait metadata.  Every supplied row is decoded.  g_host f32[rows, n]. */
-int jxb_decode_packed_meta(jxb_model* m, const uint8_t* packed_host, size_t bps, size_t rows, size_t n_full,
-                           const int64_t* sample_idx_host, const float* row_mean_host, float* g_host);
+/* Decode through a caller-supplied value LUT per row (row_lut_host f32[rows, 4], indexed by the PLINK code 00 / 01 =
+ * missing / 10 / 11) with NO centring; every supplied row is decoded.  g_host f32[rows, n].  Serves
+ * BedChunkReaderFromMeta.next_chunk_prepared (src/io/gfreader.rs:7623-7730: [(0 - mean), 0, (1 - mean), (2 - mean)], mean =
+ * 2 * ALT frequency of the shared per-trait metadata) and the raw BedChunkReader.next_chunk (src/io/gfreader.rs:3319-3440,
+ * process_snp_row src/io/gfcore.rs:405-480: [0, imputed, 1, 2], reversed when the row is flipped to the minor allele). */
+int jxb_decode_packed_lut(jxb_model* m, const uint8_t* packed_host, size_t bps, size_t rows, size_t n_full,
+                          const int64_t* sample_idx_host, const float* row_lut_host, float* g_host);
 
 /* Debug: rows [row0, row0 + rows) of the rotated block of the last scan, INCLUDING the zero padding of every row
  * (rot_host f32[rows, round_up(n, 32)], compacted row order).  Parity tests compare it with the oracle's rotation. */

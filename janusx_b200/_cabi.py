@@ -89,7 +89,7 @@ SYMBOLS = {
                                     _vp, _vp, _psz]),
     "jxb_decode_packed_prepared": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_size_t, _vp, _vp, _vp, C.c_int, _vp,
                                              _psz]),
-    "jxb_decode_packed_meta": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_size_t, _vp, _vp, _vp]),
+    "jxb_decode_packed_lut": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_size_t, _vp, _vp, _vp]),
     "jxb_debug_fetch_rot": (C.c_int, [_vp, C.c_size_t, C.c_size_t, _vp]),
     "jxb_set_timing": (None, [C.c_int]),
     "jxb_last_stage_ms": (C.c_int, [_vp, _pf]),

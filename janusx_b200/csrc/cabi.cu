@@ -1102,9 +1102,9 @@ int jxb_decode_packed_prepared(jxb_model* h, const uint8_t* packed, size_t bps, 
     return 0;
 }
 
-int jxb_decode_packed_meta(jxb_model* h, const uint8_t* packed, size_t bps, size_t rows, size_t n_full, const int64_t* sidx,
-                           const float* row_mean_host, float* g_host) {
-    if (!h || !packed || !row_mean_host || !g_host) return fail(-2, "null argument");
+int jxb_decode_packed_lut(jxb_model* h, const uint8_t* packed, size_t bps, size_t rows, size_t n_full, const int64_t* sidx,
+                          const float* row_lut_host, float* g_host) {
+    if (!h || !packed || !row_lut_host || !g_host) return fail(-2, "null argument");
     if (bps != (n_full + 3) / 4) return fail(-2, "bytes_per_snp must equal ceil(n_full/4)");
     if (!sidx && n_full != h->m.n) return fail(-2, "sample_ids length != expected sample count");
     if (rows == 0) return 0;
@@ -1119,11 +1119,13 @@ int jxb_decode_packed_meta(jxb_model* h, const uint8_t* packed, size_t bps, size
         if (rc) return rc;
         sidx_dev = m.sample_idx;
     }
-    JXB_CUDA_OK(cudaMemcpyAsync(h->prep_af, row_mean_host, rows * sizeof(float), cudaMemcpyHostToDevice, m.stream));
+    // the 4-float LUT rows travel in the out buffer's head (f64[cap][8] = room for 16 floats per row)
+    float* lut_dev = reinterpret_cast<float*>(m.out);
+    JXB_CUDA_OK(cudaMemcpyAsync(lut_dev, row_lut_host, rows * 4 * sizeof(float), cudaMemcpyHostToDevice, m.stream));
     rc = ensure_stage_f32(m, rows * n);
     if (rc) return rc;
     rc = launch_decode_center(m.packed, bps, nullptr, nullptr, rows, n_full, sidx_dev, n, m.af, m.counts, 0, nullptr, 0,
-                              m.stage_f32, n, m.stream, h->prep_af);
+                              m.stage_f32, n, m.stream, lut_dev);
     note_launch(1);
     if (rc) return rc;
     JXB_CUDA_OK(cudaMemcpyAsync(g_host, m.stage_f32, rows * n * sizeof(float), cudaMemcpyDeviceToHost, m.stream));

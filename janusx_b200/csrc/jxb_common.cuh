@@ -101,7 +101,7 @@ int launch_decode_center(const uint8_t* packed, size_t bps, const int32_t* src_r
                          size_t max_rows, size_t n_full, const int64_t* sample_idx, size_t n,
                          const float* af_by_src, const int32_t* counts_by_src, int model_code,
                          double* g64, size_t ldk, float* g32, size_t ld32, cudaStream_t st,
-                         const float* meta_mean = nullptr /* by source row: decode with LUT [0-mean, 0, 1-mean, 2-mean], no centring */);
+                         const float* row_lut = nullptr /* [rows][4] by source row and PLINK code: decode through it, no centring */);
 int launch_widen_f32(const float* src, size_t ld_src, size_t rows, size_t n, double* dst, size_t ldk,
                      cudaStream_t st);
 // out: transposed ? rotT-style [n][ld] : row-major [rows][ld]

@@ -176,21 +176,20 @@ __global__ void __launch_bounds__(256) decode_center_kernel(const uint8_t* __res
                                                             const int32_t* __restrict__ counts_by_src, int model,
                                                             double* __restrict__ g64, size_t ldk,
                                                             float* __restrict__ g32, size_t ld32,
-                                                            const float* __restrict__ meta_mean) {
+                                                            const float* __restrict__ row_lut) {
     const int rows = n_kept ? min(*n_kept, max_rows) : max_rows;
     for (int r = blockIdx.x; r < rows; r += gridDim.x) {
         const int src = src_row ? src_row[r] : r;
         const uint8_t* row = packed + (size_t)src * bps;
         float c0, c1, c2, c3;
-        if (meta_mean) {
-            // BedChunkReaderFromMeta (src/io/gfreader.rs:7623-7730; decode_standardized_packed_block_rows_f32_with_plan,
-            // src/math/bedmath.rs:1161-1230 with inv_sd = 1, flip = false): value LUT [(0 - mean), 0, (1 - mean), (2 - mean)]
-            // in f32 with the caller's row mean; missing calls decode to 0; no re-centring
-            const float mg = meta_mean[src];
-            c0 = __fmul_rn(__fsub_rn(0.0f, mg), 1.0f);
-            c1 = 0.0f;
-            c2 = __fmul_rn(__fsub_rn(1.0f, mg), 1.0f);
-            c3 = __fmul_rn(__fsub_rn(2.0f, mg), 1.0f);
+        if (row_lut) {
+            // caller-supplied value LUT per source row, indexed by the 2-bit PLINK code (00, 01 = missing, 10, 11); no
+            // centring.  Serves BedChunkReaderFromMeta (src/io/gfreader.rs:7623-7730: [(0-m), 0, (1-m), (2-m)]) and the raw
+            // BedChunkReader.next_chunk (src/io/gfcore.rs:405-480: [0, imputed, 1, 2] or flipped [2, imputed, 1, 0])
+            c0 = row_lut[4 * src + 0];
+            c1 = row_lut[4 * src + 1];
+            c2 = row_lut[4 * src + 2];
+            c3 = row_lut[4 * src + 3];
         } else {
         // decode.rs:218-219: mean_g = (2.0 * maf as f64).max(0.0) as f32; row_flip (bit 1 of the keep word, set only from
         // prepared row metadata) reverses the raw LUT to [2, mean_g, 1, 0] (decode.rs:163-178)
@@ -282,12 +281,12 @@ int launch_compact(const int32_t* counts, size_t rows, int32_t* src_row, int32_t
 int launch_decode_center(const uint8_t* packed, size_t bps, const int32_t* src_row, const int32_t* n_kept,
                          size_t max_rows, size_t n_full, const int64_t* sample_idx, size_t n,
                          const float* af_by_src, const int32_t* counts_by_src, int model_code, double* g64,
-                         size_t ldk, float* g32, size_t ld32, cudaStream_t st, const float* meta_mean) {
+                         size_t ldk, float* g32, size_t ld32, cudaStream_t st, const float* row_lut) {
     if (max_rows == 0) return 0;
     const int blocks = (int)std::min<size_t>(max_rows, 148 * 16);
     decode_center_kernel<<<blocks, 256, 0, st>>>(packed, bps, src_row, n_kept, (int)max_rows, (int)n_full,
                                                  sample_idx, (int)n, af_by_src, counts_by_src, model_code, g64, ldk,
-                                                 g32, ld32, meta_mean);
+                                                 g32, ld32, row_lut);
     JXB_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -7,7 +7,7 @@ The per-row QC of this route is NOT the unified scan's f32 arithmetic: it runs i
 (process_snp_row_with_precomputed_counts_impl, src/io/gfcore.rs:405-480).  The counts are exact integers, so they come
 from the device (jxb_decode_packed), the handful of f64 expressions per row is evaluated here exactly as the reference
 writes them, and the decode / impute / centre of the kept rows runs on the device (jxb_decode_packed_prepared).
-Not built: raw `next_chunk`, bim_range / snp_sites / chr_keys / bp_min / bp_max / ranges selectors, the windowed mmap,
+Not built: bim_range / snp_sites / chr_keys / bp_min / bp_max / ranges selectors, the windowed mmap, fill_missing = False,
 non-additive codings (their value map applies a 1e-6 tolerance to the imputed dosage, src/io/gfreader.rs:3161-3186).
 """
 from __future__ import annotations
@@ -58,6 +58,37 @@ def prepared_row_decisions(missing, het, hom_alt, n: int, maf_thr: float, miss_t
         imputed = (alt_sum / non_missing.astype(np.float64)).astype(np.float32)
     imputed = np.where(empty, np.float32(0.0), imputed).astype(np.float32)   # all-missing rows are filled with 0
     return keep, imputed
+
+
+def raw_row_decisions(missing, het, hom_alt, n: int, maf_thr: float, miss_thr: float, het_thr: float):
+    """process_snp_row (src/io/gfcore.rs:405-480 with preserve_alt_orientation = false, fill_missing = true) on integer
+    counts -> (keep bool[m], flip bool[m], lut f32[m, 4]): rows whose ALT frequency exceeds 0.5 are recoded to the other
+    allele (g -> 2 - g, alleles swapped by the caller); missing calls take the mean dosage of the (recoded) row."""
+    missing = np.asarray(missing, dtype=np.int64)
+    het = np.asarray(het, dtype=np.int64)
+    hom = np.asarray(hom_alt, dtype=np.int64)
+    maf_t, miss_t, het_t = np.float32(maf_thr), np.float32(miss_thr), np.float32(het_thr)
+    non_missing = n - missing
+    raw_alt = (het + 2 * hom).astype(np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        missing_rate = (1.0 - non_missing.astype(np.float64) / float(n)).astype(np.float32)
+        keep = ~(missing_rate > miss_t)
+        empty = non_missing == 0
+        keep &= ~(empty & (maf_t > 0))
+        if het_t < np.float32(1.0):
+            keep &= ~(~empty & ((het.astype(np.float64) / non_missing.astype(np.float64)) > np.float64(het_t)))
+        alt_freq = raw_alt / (2.0 * non_missing.astype(np.float64))
+        flip = ~empty & (alt_freq > 0.5)
+        alt_sum = np.where(flip, 2.0 * non_missing.astype(np.float64) - raw_alt, raw_alt)
+        maf = np.minimum(alt_freq, 1.0 - alt_freq).astype(np.float32)
+        keep &= ~(~empty & (maf < maf_t))
+        imputed = np.where(empty, 0.0, alt_sum / non_missing.astype(np.float64)).astype(np.float32)
+    lut = np.empty((missing.shape[0], 4), dtype=np.float32)
+    lut[:, 0] = np.where(flip, np.float32(2.0), np.float32(0.0))
+    lut[:, 1] = imputed
+    lut[:, 2] = np.float32(1.0)
+    lut[:, 3] = np.where(flip, np.float32(0.0), np.float32(2.0))
+    return keep, flip, lut
 
 
 class BedChunkReader:
@@ -180,6 +211,41 @@ class BedChunkReader:
             rows = self._snp_indices[self._cursor:self._cursor + count]
         self._cursor += int(rows.shape[0])
         return rows
+
+    def _decode_lut(self, packed: np.ndarray, lut: np.ndarray) -> np.ndarray:
+        g = np.empty((packed.shape[0], self.n_samples), dtype=np.float32)
+        lut = np.ascontiguousarray(lut, dtype=np.float32)
+        check(lib().jxb_decode_packed_lut(self._dev.handle, ptr(packed), packed.shape[1], packed.shape[0], self._n_full,
+                                          None if self._identity else ptr(self._sidx), ptr(lut), ptr(g)))
+        return g
+
+    def next_chunk(self, chunk_size: int):
+        """src/io/gfreader.rs:3319-3440 -> None at the end, else (dosage f32[m, n], sites): rows that pass the reader's
+        thresholds, recoded to the minor allele where the ALT frequency exceeds 0.5 (alleles swapped in the returned site),
+        missing calls filled with the row mean.  Counts and decode on the device, the f64 row decisions on the host."""
+        if chunk_size == 0:
+            raise ValueError("chunk_size must be > 0")
+        n = self.n_samples
+        if n == 0:
+            return None
+        sidx = None if self._identity else self._sidx
+        blocks, sites, m = [], [], 0
+        while m < chunk_size and self._cursor < self.n_snps:
+            rows = self._source_rows(chunk_size - m)
+            packed = np.ascontiguousarray(self._packed[rows])
+            counts, _, _, _ = self._dev.decode_packed(packed, self._n_full, sidx, 0.0, 1.0, 0.0, want_g=False)
+            keep, flip, lut = raw_row_decisions(counts[:, 0], counts[:, 1], counts[:, 2], n, self.maf, self.miss, self.het)
+            k = np.nonzero(keep)[0]
+            if k.size == 0:
+                continue
+            blocks.append(self._decode_lut(np.ascontiguousarray(packed[k]), lut[k]))
+            for i in k:
+                st = self._sites[int(rows[i])]
+                sites.append(ChunkSite(st.chrom, st.pos, st.snp, st.alt_allele, st.ref_allele) if flip[i] else st)
+            m += int(k.size)
+        if m == 0:
+            return None
+        return np.concatenate(blocks), sites
 
     def next_chunk_prepared(self, chunk_size: int, coding: Optional[str] = None, snps_only: bool = False):
         """-> None at the end, else (geno_centered f32[m, n], sites, af f32[m], miss f32[m]); m <= chunk_size rows that
@@ -369,7 +435,7 @@ class BedChunkReaderFromMeta(BedChunkReader):
         return int(self._rows.shape[0])
 
     def next_chunk(self, *_a, **_k):
-        raise NotImplementedError("BedChunkReaderFromMeta only serves next_chunk_prepared (like the reference)")
+        raise AttributeError("BedChunkReaderFromMeta has no next_chunk (the reference class only serves next_chunk_prepared)")
 
     def next_chunk_prepared(self, chunk_size, coding=None, snps_only=False):
         if int(chunk_size) <= 0:
@@ -392,8 +458,8 @@ class BedChunkReaderFromMeta(BedChunkReader):
         src = self._rows[meta_idx]
         packed = np.ascontiguousarray(self._packed[src])
         mean = np.ascontiguousarray(self._row_alt_mean[meta_idx])
-        g = np.empty((src.shape[0], self.n_samples), dtype=np.float32)
-        check(lib().jxb_decode_packed_meta(self._dev.handle, ptr(packed), packed.shape[1], packed.shape[0], self._n_full,
-                                           None if self._identity else ptr(self._sidx), ptr(mean), ptr(g)))
+        # bedmath.rs:1161-1230 with inv_sd = 1, flip = false: [(0 - mean), 0 (missing), (1 - mean), (2 - mean)] in f32
+        lut = np.stack([np.float32(0.0) - mean, np.zeros_like(mean), np.float32(1.0) - mean, np.float32(2.0) - mean], axis=1)
+        g = self._decode_lut(packed, lut)
         sites = [self._sites[int(j)] for j in src]
         return g, sites, (mean * np.float32(0.5)).astype(np.float32), np.ascontiguousarray(self._row_missing[meta_idx])

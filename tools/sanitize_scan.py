@@ -34,5 +34,8 @@ jxrs._cabi.lib().jxb_set_fixed_lane_min_rows(1 << 40)
 b = mdl.scan_packed(case.packed, n, mode="lmm2", init=l10, nullml=nullml, **kw)[3]
 f2 = mdl.scan_packed(case.packed, n, mode="fvlmm", log10_lbd=l10)[3]
 d = mdl.scan_packed(case.packed, n, genetic_model="dom", **kw)[3]      # FP64 DMMA rotation
-assert np.array_equal(a, b, equal_nan=True) and np.array_equal(f, f2, equal_nan=True) and np.isfinite(d[:, 1]).any()
+# lane and warp kernels take ln|V| differently (table log of 16-sample products vs log per sample): same statistics to ~1e-9
+ok = ~np.isnan(b[:, 0])
+assert np.array_equal(np.isnan(a), np.isnan(b)) and np.allclose(a[ok, :2], b[ok, :2], rtol=1e-7, atol=0)
+assert np.array_equal(f, f2, equal_nan=True) and np.isfinite(d[:, 1]).any()
 print("sanitize_scan ok", a.shape, f.shape, d.shape)
