@@ -193,8 +193,14 @@ def test_raw_next_chunk_minor_allele_recoding(jx, oracle, tmp_path):
     bit-identical to a row-by-row restatement."""
     from janusx_b200 import synth
     case = make_problem(n=130, m=260, q=0, seed=4, missing_rate=0.04)
-    packed = case.packed.copy()
-    packed[::3] ^= np.uint8(0b10101010)                 # 00 <-> 10 and 01 <-> 11: pushes many rows above ALT frequency 0.5
+    n = case.n
+    codes0 = np.stack([(case.packed[:, j // 4] >> ((j % 4) * 2)) & 3 for j in range(4 * case.packed.shape[1])], axis=1)
+    swap = np.array([3, 1, 2, 0], dtype=np.uint8)       # hom-ref <-> hom-alt: every third row gets ALT frequency > 0.5
+    codes0[::3] = swap[codes0[::3]]
+    codes0[:, n:] = 0
+    packed = np.zeros_like(case.packed)
+    for k in range(4):
+        packed |= (codes0[:, k::4].astype(np.uint8) << (2 * k))
     prefix = str(tmp_path / "p")
     synth.write_plink(prefix, packed, case.n)
     rd = jx.BedChunkReader(prefix, maf_threshold=0.03, max_missing_rate=0.2)
@@ -205,7 +211,6 @@ def test_raw_next_chunk_minor_allele_recoding(jx, oracle, tmp_path):
             break
         gs.append(out[0]); names += [s.snp for s in out[1]]; alleles += [(s.ref_allele, s.alt_allele) for s in out[1]]
     g = np.concatenate(gs)
-    n = case.n
     codes = np.stack([(packed[:, j // 4] >> ((j % 4) * 2)) & 3 for j in range(n)], axis=1)
     want_rows, want_names, flips = [], [], 0
     for i in range(packed.shape[0]):
