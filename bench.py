@@ -68,6 +68,9 @@ def parse_args():
     ap.add_argument("--overlap", type=int, default=int(os.environ.get("JXB_BENCH_OVERLAP", 0)),
                     help="1 = streamed scan: rotation slabs under one persistent solve kernel (measured slower: both kernels "
                          "are bound by the shared-memory pipe); 0 = rotate then solve (default)")
+    ap.add_argument("--prefix", type=int, default=1,
+                    help="1 (default) = the three SNP-independent leading evaluations of every REML search come from per-batch "
+                         "tables; 0 = every evaluation in the lane kernel (same results)")
     ap.add_argument("--slab", type=int, default=int(os.environ.get("JXB_BENCH_SLAB", 0)), help="rows per rotation slab")
     return ap.parse_args()
 
@@ -409,6 +412,7 @@ def main():
     lib = _cabi.lib()
     lib.jxb_set_rotate_variant(args.rotate_variant)
     lib.jxb_set_stream_overlap(args.overlap, args.slab)
+    lib.jxb_set_prefix_evals(1 if args.prefix else 0)
     # rotate X, y and fit the null on the device (pyBLUP/assoc.py:1818-1876)
     t0 = time.perf_counter()
     mdl = jxrs.DeviceModel(s_np, np.ones((n, p)), np.zeros(n), u_t_dev, device=local_rank, u_t_on_device=True)
@@ -558,7 +562,10 @@ def main():
     _, _, _, _, evals = mdl.scan_fetch(last_rows, cols)
     mean_evals = float(evals.mean()) if evals.size and args.model != "fvlmm" else 0.0
     cached = 0 if args.model == "fvlmm" else (2 if (args.model == "lmm2" or nullml is not None) else 1)
-    exec_evals = float(np.maximum(evals - cached, 0).mean()) if evals.size and args.model != "fvlmm" else 0.0
+    # the three leading REML abscissae are the same for every SNP: evaluated from per-batch tables (SNP column only)
+    shared = 3 if (args.prefix and args.model != "fvlmm" and evals.size >= 2048) else 0
+    shared_evals = float(np.minimum(np.maximum(evals - cached, 0), shared).mean()) if evals.size and shared else 0.0
+    exec_evals = float(np.maximum(evals - cached - shared, 0).mean()) if evals.size and args.model != "fvlmm" else 0.0
     kept_last = int(evals.size)
 
     # e2e: same job through the C-ABI call with pinned HOST buffers (H2D + D2H inside the timed region)
@@ -594,7 +601,7 @@ def main():
         rot_s = st.get("rotate", 0.0) * 1e-3
         flop_per_eval = n * (3 * d * (d + 1) / 2 + 5 * d + 3 + 2)   # + 1 divide + 1 log per sample
         solve_flop = mean_evals * flop_per_eval * kept_rank
-        solve_flop_exec = exec_evals * flop_per_eval * kept_rank
+        solve_flop_exec = (exec_evals * flop_per_eval + shared_evals * n * (4 * d + 6)) * kept_rank
         # the solve TUs are compiled without FMA contraction (reference rounding): ceiling = separate DMUL/DADD issue
         # rate measured in this run (jxb_fp64_probe), charged as 1 flop per instruction; FMA-rate x2 given for context
         fp64_issue = min(fp64_rates[1], fp64_rates[2]) if fp64_rates else None
@@ -658,6 +665,10 @@ def main():
             "roofline": dominant, "roofline_rotation": rot_roof, "roofline_solve": solve_roof,
             "stage_ms_last_step_rank0": st, "wall_ms_per_step": wall_ms / args.steps,
             "solve": {"mean_objective_evals_per_snp": mean_evals, "executed_evals_per_snp": exec_evals,
+                      "shared_abscissa_evals_per_snp": shared_evals,
+                      "shared_abscissa_note": "first three abscissae of every REML search are SNP-independent: 1/(s+lambda), the "
+                                              "covariate sums and sum ln v come from per-batch tables, (4d+6)n flop per SNP "
+                                              "instead of the full evaluation; counted at that cost in frac_executed",
                       "note": "the reference's final_beta_se / ml_loglike passes (and LMM2's first ML evaluation) repeat an "
                               "abscissa already evaluated: counted by both sides, executed once here"},
             "decode": {"hbm_gb_per_s": ((shard_rows * bps + kept_rank * n * (8 if args.rotate_variant == 0 else 3))

@@ -213,6 +213,13 @@ void jxb_set_big_solve_kernel(int variant);
  * (tests compare the two); jxb_selftest_rcp compares `count` pseudo-random values with binary exponents in
  * [lo_exp, hi_exp] (extreme mantissas included) and returns the number of differing bit patterns. */
 void jxb_set_generic_divide(int on);
+/* The first three abscissae of every per-SNP REML search (src/math/brent.rs:16-136 started at the same point of the same
+ * interval: x0, the golden-section step, then one of two golden-section steps) do not depend on the SNP.  The lane-per-SNP
+ * solve therefore evaluates them for the whole batch ahead of the searches, taking 1/(s_i + lambda), the covariate block of
+ * Z'V^-1 Z, Z'V^-1 y and sum ln v from per-batch tables; only the SNP column's sums are formed per SNP.  Same operations
+ * in the same order, bit-identical results and evaluation counts.  1 (default) = batches of at least 2048 kept SNPs,
+ * 2 = every batch the lane-per-SNP kernel handles, 0 = off (tests compare). */
+void jxb_set_prefix_evals(int on);
 /* fixed-lambda batches with at least this many rows use the lane-per-SNP kernel (one HBM-bound pass over the rotated
  * block; default 4096); smaller ones the warp-per-SNP kernel.  Same ordered sums, identical results. */
 void jxb_set_fixed_lane_min_rows(size_t rows);

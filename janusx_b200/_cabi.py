@@ -13,7 +13,7 @@ from pathlib import Path
 import numpy as np
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libjxb200.so"
+LIB_PATH = Path(os.environ["JXB_LIB_PATH"]) if os.environ.get("JXB_LIB_PATH") else _PKG / "libjxb200.so"   # override: kernel A/B builds
 _lib = None
 
 
@@ -100,6 +100,7 @@ SYMBOLS = {
     "jxb_set_big_solve_kernel": (None, [C.c_int]),
     "jxb_set_stream_overlap": (None, [C.c_int, C.c_size_t]),
     "jxb_set_generic_divide": (None, [C.c_int]),
+    "jxb_set_prefix_evals": (None, [C.c_int]),
     "jxb_set_fixed_lane_min_rows": (None, [C.c_size_t]),
     "jxb_selftest_rcp": (C.c_int, [C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_uint64)]),
     "jxb_last_stage_ms8": (C.c_int, [_vp, _pf]),

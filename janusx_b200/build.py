@@ -9,7 +9,7 @@ from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
-OUT = PKG / "libjxb200.so"
+OUT = Path(os.environ["JXB_BUILD_OUT"]) if os.environ.get("JXB_BUILD_OUT") else PKG / "libjxb200.so"   # override: kernel A/B builds
 # (source, object stem, extra defines).  k3_inst.cu is compiled once per static covariate count so the
 # heavy fully-unrolled K3 kernels build in parallel.
 UNITS = [("cabi.cu", "cabi", []), ("k1_decode.cu", "k1_decode", []), ("k2_rotate.cu", "k2_rotate", []), ("k2_int8.cu", "k2_int8", []), ("k2_i8mma.cu", "k2_i8mma", []),
@@ -48,8 +48,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not needs_build():
         return OUT
     nvcc = _nvcc()
-    objdir = PKG / "build"
-    objdir.mkdir(exist_ok=True)
+    objdir = Path(os.environ["JXB_BUILD_OBJDIR"]) if os.environ.get("JXB_BUILD_OBJDIR") else PKG / "build"
+    objdir.mkdir(parents=True, exist_ok=True)
     env = dict(os.environ)
     # the image exports CC/CXX pointing at a gcc wrapper without OpenMP specs; nvcc wants the system g++
     ccbin = "/usr/bin/g++" if Path("/usr/bin/g++").exists() else shutil.which("g++")

@@ -616,6 +616,7 @@ void jxb_set_rotate_variant(int variant) { g_rotate_variant = variant; }
 void jxb_set_thread_solve_min_rows(size_t rows) { g_thread_solve_min_rows = rows; }
 void jxb_set_big_solve_kernel(int variant) { g_big_solve_kernel = variant == 1 ? 1 : 0; }
 void jxb_set_generic_divide(int on) { g_force_generic_divide = on ? 1 : 0; }
+void jxb_set_prefix_evals(int on) { g_prefix_evals = on == 2 ? 2 : (on ? 1 : 0); }
 void jxb_set_fixed_lane_min_rows(size_t rows) { g_fixed_lane_min_rows = rows; }
 
 int jxb_selftest_rcp(size_t count, int lo_exp, int hi_exp, uint64_t* mismatches) {
@@ -667,7 +668,7 @@ void jxb_model_destroy(jxb_model* h) {
     Model& m = h->m;
     cudaSetDevice(m.device);
     if (m.stream) cudaStreamSynchronize(m.stream);
-    void* ptrs[] = {m.s, m.y, m.xt, m.rec, m.ut, m.g64, m.rot, m.log_table, m.ssq, m.out, m.evals, m.packed, m.counts, m.af, m.src_row,
+    void* ptrs[] = {m.s, m.y, m.xt, m.rec, m.ut, m.g64, m.rot, m.log_table, m.ssq, m.prefix_buf, m.out, m.evals, m.packed, m.counts, m.af, m.src_row,
                     m.n_kept, m.sample_idx, m.stage_f32, m.fx_w, m.fx_py, m.fx_wx, m.fx_scal, m.fx_rec, h->missr, h->mask,
                     h->prep_af, h->prep_flip,
                     h->scal, m.q8, m.q8_inv_scale, m.q8_rk, m.a8, m.coef, m.flags8, m.c32, m.lt_ws, m.corr64};

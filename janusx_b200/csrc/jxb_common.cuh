@@ -78,6 +78,7 @@ struct Model {
     void* tmap_a8 = nullptr; size_t tmap_a8_rows = 0; void* tmap_q8_7 = nullptr; void* tmap_q8_3 = nullptr;
     void* log_table = nullptr;                           // k3::LogTable (thread-per-SNP solve)
     double* ssq = nullptr; size_t ssq_cap = 0;           // per-row sum of squares (lane-per-SNP solve)
+    double* prefix_buf = nullptr; size_t prefix_cap = 0; // tables + per-SNP slots of the shared-abscissa evaluations (doubles)
     // fixed-lambda cache (A14)
     float* fx_w = nullptr; float* fx_py = nullptr; float* fx_wx = nullptr; double* fx_scal = nullptr;
     double* fx_rec = nullptr;                            // [ldn][round_up(p+2,2)] interleaved f64 records (p <= 8)
@@ -118,6 +119,7 @@ int launch_solve_lane(Model& m, const float* rot, size_t ldc, size_t max_rows, c
                       const SolveParams& sp, double* out, int out_cols, int32_t* evals, int32_t* queue, cudaStream_t st);
 int rcp_selftest(size_t count, int lo_exp, int hi_exp, unsigned long long* mismatches_host);
 extern int g_force_generic_divide;
+extern int g_prefix_evals;
 extern size_t g_fixed_lane_min_rows;
 // streamed scan: solve while later row slabs are still being rotated (k3_solve.cu / cabi.cu scan_streamed)
 int ensure_solve_lane_buffers(Model& m, size_t max_rows, cudaStream_t st);

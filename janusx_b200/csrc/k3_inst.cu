@@ -57,26 +57,47 @@ int JXB_CAT(k3_launch_solve_thread_p, JXB_P)(const k3::ModelView& mv, const floa
 int JXB_CAT(k3_launch_solve_lane_p, JXB_P)(const k3::ModelView& mv, int sms, const float* rot, size_t ldc, int max_rows,
                                            const int32_t* n_rows_dev, const SolveParams& sp, double* out, int out_cols,
                                            int32_t* evals, const void* log_table, double* ssq, int32_t* queue,
-                                           int fast_rcp, cudaStream_t st) {
+                                           int fast_rcp, const k3::PrefixTables* prefix, cudaStream_t st) {
     constexpr int kSmem = 4 * (int)sizeof(k3::ThreadTile<JXB_P, JXB_K3L_TILE>);
+    constexpr int kSmemPrefix = 4 * (int)sizeof(k3::PrefixTile<JXB_P>);
     constexpr int kPerSm = (JXB_P <= 4) ? JXB_K3T_MINB : 3;
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(k3::solve_lane_kernel<JXB_P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
         cudaFuncSetAttribute(k3::solve_lane_kernel<JXB_P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+        cudaFuncSetAttribute(k3::prefix_eval_kernel<JXB_P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPrefix);
+        cudaFuncSetAttribute(k3::prefix_eval_kernel<JXB_P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPrefix);
         attr = true;
     }
     k3::row_ssq_kernel<<<sms * 8, 256, 0, st>>>(rot, ldc, mv.n, max_rows, n_rows_dev, ssq);
     cudaMemsetAsync(queue, 0, sizeof(int32_t), st);
+    const double* slots = nullptr;
+    if (prefix) {
+        // tables of the SNP-independent abscissae, then the three leading evaluations of every SNP (k3_solve.cuh)
+        slots = prefix->slots;
+        cudaMemsetAsync(prefix->slots, 0xFF, (size_t)max_rows * k3::kPrefixEvals * 6 * sizeof(double), st);   // NaN = empty
+        const int pblocks = (max_rows + 127) / 128;
+        if (fast_rcp) {
+            k3::prefix_table_kernel<JXB_P, true><<<1, 128, 0, st>>>(mv, sp, (const k3::LogTable*)log_table, *prefix);
+            k3::prefix_eval_kernel<JXB_P, true><<<pblocks, 128, kSmemPrefix, st>>>(mv, *prefix, rot, ldc, max_rows, n_rows_dev, sp,
+                                                                                  (const k3::LogTable*)log_table, ssq);
+        } else {
+            k3::prefix_table_kernel<JXB_P, false><<<1, 128, 0, st>>>(mv, sp, (const k3::LogTable*)log_table, *prefix);
+            k3::prefix_eval_kernel<JXB_P, false><<<pblocks, 128, kSmemPrefix, st>>>(mv, *prefix, rot, ldc, max_rows, n_rows_dev, sp,
+                                                                                   (const k3::LogTable*)log_table, ssq);
+        }
+    }
     const int blocks = std::min((max_rows + 127) / 128, sms * kPerSm);   // persistent: lanes refill from the queue
     if (fast_rcp)
         k3::solve_lane_kernel<JXB_P, true><<<blocks, 128, kSmem, st>>>(mv, rot, ldc, max_rows, n_rows_dev, sp, out, out_cols, evals,
-                                                                      (const k3::LogTable*)log_table, ssq, queue);
+                                                                      (const k3::LogTable*)log_table, ssq, queue, slots);
     else
         k3::solve_lane_kernel<JXB_P, false><<<blocks, 128, kSmem, st>>>(mv, rot, ldc, max_rows, n_rows_dev, sp, out, out_cols, evals,
-                                                                       (const k3::LogTable*)log_table, ssq, queue);
+                                                                       (const k3::LogTable*)log_table, ssq, queue, slots);
     return 0;
 }
+
+int JXB_CAT(k3_prefix_table_doubles_p, JXB_P)() { return 4 * k3::PrefixDims<JXB_P>::NS; }
 
 // Streamed (co-resident) lane kernel: 3 CTAs per SM, 16-sample tiles.  `sync` = {queue, ready, abort} (zeroed by the caller).
 int JXB_CAT(k3_launch_solve_lane_stream_p, JXB_P)(const k3::ModelView& mv, int sms, const float* rot, size_t ldc,

@@ -16,7 +16,8 @@ namespace jxb {
                                     const SolveParams&, double*, int, int32_t*, const void*, cudaStream_t);    \
     int k3_launch_solve_lane_p##P(const k3::ModelView&, int, const float*, size_t, int, const int32_t*,        \
                                   const SolveParams&, double*, int, int32_t*, const void*, double*, int32_t*,  \
-                                  int, cudaStream_t);                                                          \
+                                  int, const k3::PrefixTables*, cudaStream_t);                                 \
+    int k3_prefix_table_doubles_p##P();                                                                        \
     int k3_launch_solve_lane_stream_p##P(const k3::ModelView&, int, const float*, size_t, int, const SolveParams&, \
                                          double*, int, int32_t*, const void*, const double*, int32_t*, cudaStream_t); \
     int k3_solve_lane_stream_res_p##P(int*, int*);                                                             \
@@ -27,6 +28,8 @@ JXB_DECL_P(1) JXB_DECL_P(2) JXB_DECL_P(3) JXB_DECL_P(4) JXB_DECL_P(5) JXB_DECL_P
 
 size_t g_fixed_lane_min_rows = 4096;   // fixed-lambda batches at least this large use the lane-per-SNP kernel
 int g_force_generic_divide = 0;   // tests: compare the rcp_fast kernels with the compiler-divide kernels
+int g_prefix_evals = 1;           // lane-per-SNP solve: take the SNP-independent leading evaluations from shared tables (2 = any batch)
+size_t g_prefix_min_rows = 2048;  // ... for batches at least this large (two extra launches)
 
 namespace {
 
@@ -159,7 +162,36 @@ int launch_solve_lane(Model& m, const float* rot, size_t ldc, size_t max_rows, c
         const double lo = *mm.first + pow(10.0, std::min(sp.low, sp.high)), hi = *mm.second + pow(10.0, std::max(sp.low, sp.high));
         fast = std::isfinite(lo) && std::isfinite(hi) && lo >= 1e-290 && hi <= 1e290;
     }
-#define L_STATIC(P) k3_launch_solve_lane_p##P(mv, sms, rot, ldc, (int)max_rows, n_rows_dev, sp, out, out_cols, evals, m.log_table, m.ssq, queue, fast, st)
+    // shared-abscissa prefix (k3_solve.cuh prefix_eval_kernel): one allocation {xs[8] | sums | vb[n_pad] | rec[3][n_pad][rs] | slots}
+    PrefixTables pt{};
+    const PrefixTables* prefix = nullptr;
+    if (g_prefix_evals == 2 || (g_prefix_evals && max_rows >= g_prefix_min_rows)) {
+        const size_t n_pad = (m.n + 31) & ~(size_t)31;
+        int sums_doubles = 0;
+#define PT_STATIC(P) sums_doubles = k3_prefix_table_doubles_p##P()
+#define PT_DYN() (void)0
+        JXB_DISPATCH_P((int)m.p, PT_STATIC, PT_DYN)
+#undef PT_STATIC
+#undef PT_DYN
+        const size_t head = 8 + (((size_t)sums_doubles + 7) & ~(size_t)7);
+        const size_t rows_cap = std::max(max_rows, m.cap_rows);
+        const size_t need = head + n_pad + 3 * n_pad * m.rs + rows_cap * kPrefixEvals * 6;
+        if (m.prefix_cap < need) {
+            JXB_CUDA_OK(cudaStreamSynchronize(st));
+            if (m.prefix_buf) cudaFree(m.prefix_buf);
+            m.prefix_buf = nullptr; m.prefix_cap = 0;
+            JXB_CUDA_OK(cudaMalloc((void**)&m.prefix_buf, need * sizeof(double)));
+            m.prefix_cap = need;
+        }
+        pt.xs = m.prefix_buf;
+        pt.sums = m.prefix_buf + 8;
+        pt.vb = m.prefix_buf + head;
+        pt.rec = pt.vb + n_pad;
+        pt.slots = pt.rec + 3 * n_pad * m.rs;
+        prefix = &pt;
+        note_launch(2);   // prefix_table_kernel + prefix_eval_kernel
+    }
+#define L_STATIC(P) k3_launch_solve_lane_p##P(mv, sms, rot, ldc, (int)max_rows, n_rows_dev, sp, out, out_cols, evals, m.log_table, m.ssq, queue, fast, prefix, st)
 #define L_DYN() (void)0
     JXB_DISPATCH_P((int)m.p, L_STATIC, L_DYN)
 #undef L_STATIC

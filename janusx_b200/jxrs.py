@@ -464,6 +464,12 @@ def set_big_solve_kernel(variant: int) -> None:
     lib().jxb_set_big_solve_kernel(int(variant))
 
 
+def set_prefix_evals(mode: int) -> None:
+    """Shared-abscissa prefix of the per-SNP REML searches in the lane-per-SNP solve: 1 = batches of >= 2048 kept SNPs
+    (default), 2 = every batch, 0 = off.  Results and evaluation counts do not depend on it."""
+    lib().jxb_set_prefix_evals(int(mode))
+
+
 def set_stream_overlap(on: bool, slab_rows: int = 0) -> None:
     """Streamed scan (default on): rotate large batches in slabs while one persistent solve kernel consumes the rotated
     rows, so the tensor pipe and the FP64 pipe run concurrently.  slab_rows = 0 keeps the current slab size (8192)."""

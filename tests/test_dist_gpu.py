@@ -98,7 +98,7 @@ def test_cli_one_job_on_n_ranks_is_byte_identical(tmp_path, oracle):
             fh.write(f"S{j}\t{case.y[j]:.10f}\n")
     outs = {}
     ndev = torch.cuda.device_count()
-    counts = [1, 2, 3] if ndev < 4 else [1, 2, 4, min(8, ndev)]
+    counts = [1, 2, 3] if ndev < 4 else sorted({1, 2, 4, min(8, ndev)})
     for g in counts:
         out = tmp_path / f"out{g}"
         log = _run_cli(["-bfile", prefix, "-p", str(tmp_path / "pheno.tsv"), "-lmm", "-lmm2", "-fvlmm", "-k", "1", "-q", "2",

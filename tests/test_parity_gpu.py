@@ -508,6 +508,48 @@ def test_int8_sliced_rotation_variant(jx, oracle):
         jx.set_rotate_variant(3)
 
 
+@pytest.mark.parametrize("p_cov", [1, 4, 5, 8])
+def test_shared_abscissa_prefix_matches_plain_search(jx, oracle, p_cov):
+    """The lane-per-SNP solve takes the first three objective values of every REML search (abscissae no SNP can change:
+    src/math/brent.rs:16-136) from per-batch tables.  Forced on at a small size: same gates against the oracle, the
+    oracle's evaluation counts, and rows bit-identical to the search that evaluates everything itself -- also when the
+    search ends inside the prefix (max_iter 1..3), starts from a given point, or runs on the compiler's divide."""
+    case = make_problem(n=210, m=160, q=p_cov - 1, seed=90 + p_cov, missing_rate=0.02)
+    nm = null_model(oracle, case)
+    n = case.n
+    keep, af, _, _ = oracle.count_qc_block(case.packed, n, None, 0.02, 0.05, 1.0)
+    idx = np.nonzero(keep)[0]
+    g = oracle.decode_centered_block(case.packed, n, af[idx], row_indices=idx)
+    rot = oracle.rotate_block(g, nm["ut"])
+    _, mlnull = oracle.lmm_ml_null_brent(case.s, nm["xcov"], nm["y"], nm["low"], nm["high"], 30, 1e-2)
+    want, ev_o = oracle.lmm_reml_lmm2_chunk_f32(case.s, nm["xcov"], nm["y"], nm["low"], nm["high"], rot, mlnull, 30, 1e-2,
+                                                return_evals=True)
+    mdl = jx.DeviceModel(case.s, nm["xcov"], nm["y"], nm["ut"])
+    kw2 = dict(mode="lmm2", low=nm["low"], high=nm["high"], nullml=mlnull, return_evals=True)
+    try:
+        jx.set_thread_solve_min_rows(1)
+        jx.set_prefix_evals(2)
+        k, _, _, out, ev = mdl.scan_packed(case.packed, n, **kw2)
+        assert np.array_equal(k, keep) and np.array_equal(ev, ev_o)
+        assert_results_close(out, want, cols_p=(2, 5), cols_lambda=(3,))
+        variants = [dict(kw2), dict(kw2, max_iter=1), dict(kw2, max_iter=2), dict(kw2, max_iter=3), dict(kw2, max_iter=4),
+                    dict(kw2, init=0.37), dict(kw2, init=nm["low"]), dict(kw2, tol=1e-6, max_iter=60),
+                    dict(mode="lmm", low=nm["low"], high=nm["high"], return_evals=True),
+                    dict(mode="lmm", low=nm["low"], high=nm["high"], nullml=mlnull, max_iter=2, return_evals=True)]
+        for divide in (0, 1):
+            jx._cabi.lib().jxb_set_generic_divide(divide)
+            for v in variants:
+                jx.set_prefix_evals(2)
+                a = mdl.scan_packed(case.packed, n, **v)
+                jx.set_prefix_evals(0)
+                b = mdl.scan_packed(case.packed, n, **v)
+                assert np.array_equal(a[3], b[3], equal_nan=True) and np.array_equal(a[4], b[4]), (divide, v)
+    finally:
+        jx._cabi.lib().jxb_set_generic_divide(0)
+        jx.set_prefix_evals(1)
+        jx.set_thread_solve_min_rows(32768)
+
+
 @pytest.mark.parametrize("big_kernel", [0, 1])
 @pytest.mark.parametrize("mode", ["lmm", "lmm2"])
 def test_thread_per_snp_solve_kernel(jx, oracle, mode, big_kernel):
@@ -719,6 +761,15 @@ def test_full_batch_at_full_size_sampled_parity(jx, oracle, n, model):
         assert_results_close(got, want)
         assert np.array_equal(ev[pos[picks]], ev_o)             # the same Brent path, evaluation for evaluation
     assert not streamed
+    # the same batch without the shared-abscissa prefix (every evaluation of every search done by the lane kernel itself):
+    # bit-identical rows and evaluation counts
+    jx._cabi.lib().jxb_set_prefix_evals(0)
+    try:
+        mdl.scan_packed_dev(pk.data_ptr(), rows, bps, n, None, **kw)
+        keep0, af0, missing0, out0, ev0 = mdl.scan_fetch(rows, cols)
+    finally:
+        jx._cabi.lib().jxb_set_prefix_evals(1)
+    assert np.array_equal(keep, keep0) and np.array_equal(out, out0, equal_nan=True) and np.array_equal(ev, ev0)
     if n <= 24000:
         # the same batch with the compiler-generated divide instead of rcp_fast, and through the streamed scan (rotation
         # slabs under one persistent solve kernel): same arithmetic, bit-identical rows
