@@ -601,7 +601,7 @@ def main():
         rot_s = st.get("rotate", 0.0) * 1e-3
         flop_per_eval = n * (3 * d * (d + 1) / 2 + 5 * d + 3 + 2)   # + 1 divide + 1 log per sample
         solve_flop = mean_evals * flop_per_eval * kept_rank
-        solve_flop_exec = (exec_evals * flop_per_eval + shared_evals * n * (4 * d + 6)) * kept_rank
+        solve_flop_exec = (exec_evals * flop_per_eval + (4.0 * n * (4 * d + 6) if shared_evals > 0 else 0.0)) * kept_rank
         # the solve TUs are compiled without FMA contraction (reference rounding): ceiling = separate DMUL/DADD issue
         # rate measured in this run (jxb_fp64_probe), charged as 1 flop per instruction; FMA-rate x2 given for context
         fp64_issue = min(fp64_rates[1], fp64_rates[2]) if fp64_rates else None
@@ -666,9 +666,10 @@ def main():
             "stage_ms_last_step_rank0": st, "wall_ms_per_step": wall_ms / args.steps,
             "solve": {"mean_objective_evals_per_snp": mean_evals, "executed_evals_per_snp": exec_evals,
                       "shared_abscissa_evals_per_snp": shared_evals,
-                      "shared_abscissa_note": "first three abscissae of every REML search are SNP-independent: 1/(s+lambda), the "
-                                              "covariate sums and sum ln v come from per-batch tables, (4d+6)n flop per SNP "
-                                              "instead of the full evaluation; counted at that cost in frac_executed",
+                      "shared_abscissa_note": "first three abscissae of every REML search are SNP-independent (x0, golden step, "
+                                              "one of two golden steps): 1/(s+lambda), the covariate sums and sum ln v come from "
+                                              "per-batch tables and prefix_eval_kernel evaluates the four candidates in two sweeps, "
+                                              "4(4d+6)n flop per SNP; counted at that cost in frac_executed",
                       "note": "the reference's final_beta_se / ml_loglike passes (and LMM2's first ML evaluation) repeat an "
                               "abscissa already evaluated: counted by both sides, executed once here"},
             "decode": {"hbm_gb_per_s": ((shard_rows * bps + kept_rank * n * (8 if args.rotate_variant == 0 else 3))

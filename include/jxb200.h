@@ -217,7 +217,8 @@ void jxb_set_generic_divide(int on);
  * interval: x0, the golden-section step, then one of two golden-section steps) do not depend on the SNP.  The lane-per-SNP
  * solve therefore evaluates them for the whole batch ahead of the searches, taking 1/(s_i + lambda), the covariate block of
  * Z'V^-1 Z, Z'V^-1 y and sum ln v from per-batch tables; only the SNP column's sums are formed per SNP.  Same operations
- * in the same order, bit-identical results and evaluation counts.  1 (default) = batches of at least 2048 kept SNPs,
+ * in the same order, bit-identical results and evaluation counts (up to 6 covariate columns; 7 and 8 run plain
+ * searches).  1 (default) = batches of at least 2048 kept SNPs,
  * 2 = every batch the lane-per-SNP kernel handles, 0 = off (tests compare). */
 void jxb_set_prefix_evals(int on);
 /* fixed-lambda batches with at least this many rows use the lane-per-SNP kernel (one HBM-bound pass over the rotated

@@ -73,18 +73,16 @@ int JXB_CAT(k3_launch_solve_lane_p, JXB_P)(const k3::ModelView& mv, int sms, con
     cudaMemsetAsync(queue, 0, sizeof(int32_t), st);
     const double* slots = nullptr;
     if (prefix) {
-        // tables of the SNP-independent abscissae, then the three leading evaluations of every SNP (k3_solve.cuh)
+        // tables of the SNP-independent abscissae, then the leading evaluations of every SNP (k3_solve.cuh)
         slots = prefix->slots;
         cudaMemsetAsync(prefix->slots, 0xFF, (size_t)max_rows * k3::kPrefixEvals * 6 * sizeof(double), st);   // NaN = empty
         const int pblocks = (max_rows + 127) / 128;
         if (fast_rcp) {
             k3::prefix_table_kernel<JXB_P, true><<<1, 128, 0, st>>>(mv, sp, (const k3::LogTable*)log_table, *prefix);
-            k3::prefix_eval_kernel<JXB_P, true><<<pblocks, 128, kSmemPrefix, st>>>(mv, *prefix, rot, ldc, max_rows, n_rows_dev, sp,
-                                                                                  (const k3::LogTable*)log_table, ssq);
+            k3::prefix_eval_kernel<JXB_P, true><<<pblocks, 128, kSmemPrefix, st>>>(mv, *prefix, rot, ldc, max_rows, n_rows_dev, sp, ssq);
         } else {
             k3::prefix_table_kernel<JXB_P, false><<<1, 128, 0, st>>>(mv, sp, (const k3::LogTable*)log_table, *prefix);
-            k3::prefix_eval_kernel<JXB_P, false><<<pblocks, 128, kSmemPrefix, st>>>(mv, *prefix, rot, ldc, max_rows, n_rows_dev, sp,
-                                                                                   (const k3::LogTable*)log_table, ssq);
+            k3::prefix_eval_kernel<JXB_P, false><<<pblocks, 128, kSmemPrefix, st>>>(mv, *prefix, rot, ldc, max_rows, n_rows_dev, sp, ssq);
         }
     }
     const int blocks = std::min((max_rows + 127) / 128, sms * kPerSm);   // persistent: lanes refill from the queue
@@ -98,6 +96,7 @@ int JXB_CAT(k3_launch_solve_lane_p, JXB_P)(const k3::ModelView& mv, int sms, con
 }
 
 int JXB_CAT(k3_prefix_table_doubles_p, JXB_P)() { return 4 * k3::PrefixDims<JXB_P>::NS; }
+int JXB_CAT(k3_prefix_rec_doubles_p, JXB_P)() { return k3::PrefixDims<JXB_P>::RSF; }
 
 // Streamed (co-resident) lane kernel: 3 CTAs per SM, 16-sample tiles.  `sync` = {queue, ready, abort} (zeroed by the caller).
 int JXB_CAT(k3_launch_solve_lane_stream_p, JXB_P)(const k3::ModelView& mv, int sms, const float* rot, size_t ldc,

@@ -18,6 +18,7 @@ namespace jxb {
                                   const SolveParams&, double*, int, int32_t*, const void*, double*, int32_t*,  \
                                   int, const k3::PrefixTables*, cudaStream_t);                                 \
     int k3_prefix_table_doubles_p##P();                                                                        \
+    int k3_prefix_rec_doubles_p##P();                                                                          \
     int k3_launch_solve_lane_stream_p##P(const k3::ModelView&, int, const float*, size_t, int, const SolveParams&, \
                                          double*, int, int32_t*, const void*, const double*, int32_t*, cudaStream_t); \
     int k3_solve_lane_stream_res_p##P(int*, int*);                                                             \
@@ -162,20 +163,21 @@ int launch_solve_lane(Model& m, const float* rot, size_t ldc, size_t max_rows, c
         const double lo = *mm.first + pow(10.0, std::min(sp.low, sp.high)), hi = *mm.second + pow(10.0, std::max(sp.low, sp.high));
         fast = std::isfinite(lo) && std::isfinite(hi) && lo >= 1e-290 && hi <= 1e290;
     }
-    // shared-abscissa prefix (k3_solve.cuh prefix_eval_kernel): one allocation {xs[8] | sums | vb[n_pad] | rec[3][n_pad][rs] | slots}
+    // shared-abscissa prefix (k3_solve.cuh prefix_eval_kernel): one allocation {xs[8] | sums | rec[n_pad][rsf] | slots}
     PrefixTables pt{};
     const PrefixTables* prefix = nullptr;
-    if (g_prefix_evals == 2 || (g_prefix_evals && max_rows >= g_prefix_min_rows)) {
+    // (7 and 8 covariate columns: four abscissae x (p + 2) running sums no longer fit the register file; plain searches)
+    if (m.p <= 6 && (g_prefix_evals == 2 || (g_prefix_evals && max_rows >= g_prefix_min_rows))) {
         const size_t n_pad = (m.n + 31) & ~(size_t)31;
-        int sums_doubles = 0;
-#define PT_STATIC(P) sums_doubles = k3_prefix_table_doubles_p##P()
+        int sums_doubles = 0, rsf = 0;
+#define PT_STATIC(P) sums_doubles = k3_prefix_table_doubles_p##P(), rsf = k3_prefix_rec_doubles_p##P()
 #define PT_DYN() (void)0
         JXB_DISPATCH_P((int)m.p, PT_STATIC, PT_DYN)
 #undef PT_STATIC
 #undef PT_DYN
         const size_t head = 8 + (((size_t)sums_doubles + 7) & ~(size_t)7);
         const size_t rows_cap = std::max(max_rows, m.cap_rows);
-        const size_t need = head + n_pad + 3 * n_pad * m.rs + rows_cap * kPrefixEvals * 6;
+        const size_t need = head + n_pad * rsf + rows_cap * kPrefixEvals * 6;
         if (m.prefix_cap < need) {
             JXB_CUDA_OK(cudaStreamSynchronize(st));
             if (m.prefix_buf) cudaFree(m.prefix_buf);
@@ -185,9 +187,8 @@ int launch_solve_lane(Model& m, const float* rot, size_t ldc, size_t max_rows, c
         }
         pt.xs = m.prefix_buf;
         pt.sums = m.prefix_buf + 8;
-        pt.vb = m.prefix_buf + head;
-        pt.rec = pt.vb + n_pad;
-        pt.slots = pt.rec + 3 * n_pad * m.rs;
+        pt.rec = m.prefix_buf + head;
+        pt.slots = pt.rec + n_pad * rsf;
         prefix = &pt;
         note_launch(2);   // prefix_table_kernel + prefix_eval_kernel
     }
