@@ -120,6 +120,7 @@ int upload_small(Model& m, const double* s, const double* xcov, const double* y)
     JXB_CUDA_OK(cudaMemcpyAsync(m.xt, xt.data(), xt.size() * sizeof(double), cudaMemcpyHostToDevice, m.stream));
     JXB_CUDA_OK(cudaStreamSynchronize(m.stream));
     m.fx_valid = false;
+    m.prefix_valid = false;
     return 0;
 }
 

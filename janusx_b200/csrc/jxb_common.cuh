@@ -79,6 +79,7 @@ struct Model {
     void* log_table = nullptr;                           // k3::LogTable (thread-per-SNP solve)
     double* ssq = nullptr; size_t ssq_cap = 0;           // per-row sum of squares (lane-per-SNP solve)
     double* prefix_buf = nullptr; size_t prefix_cap = 0; // tables + per-SNP slots of the shared-abscissa evaluations (doubles)
+    bool prefix_valid = false; double prefix_key[7] = {0, 0, 0, 0, 0, 0, 0};   // tables in prefix_buf are current for this {low, high, tol, max_iter, has_init, init, divide}
     // fixed-lambda cache (A14)
     float* fx_w = nullptr; float* fx_py = nullptr; float* fx_wx = nullptr; double* fx_scal = nullptr;
     double* fx_rec = nullptr;                            // [ldn][round_up(p+2,2)] interleaved f64 records (p <= 8)

@@ -57,7 +57,7 @@ int JXB_CAT(k3_launch_solve_thread_p, JXB_P)(const k3::ModelView& mv, const floa
 int JXB_CAT(k3_launch_solve_lane_p, JXB_P)(const k3::ModelView& mv, int sms, const float* rot, size_t ldc, int max_rows,
                                            const int32_t* n_rows_dev, const SolveParams& sp, double* out, int out_cols,
                                            int32_t* evals, const void* log_table, double* ssq, int32_t* queue,
-                                           int fast_rcp, const k3::PrefixTables* prefix, cudaStream_t st) {
+                                           int fast_rcp, const k3::PrefixTables* prefix, int build_tables, cudaStream_t st) {
     constexpr int kSmem = 4 * (int)sizeof(k3::ThreadTile<JXB_P, JXB_K3L_TILE>);
     constexpr int kSmemPrefix = 4 * (int)sizeof(k3::PrefixTile<JXB_P>);
     constexpr int kPerSm = (JXB_P <= 4) ? JXB_K3T_MINB : 3;
@@ -78,10 +78,10 @@ int JXB_CAT(k3_launch_solve_lane_p, JXB_P)(const k3::ModelView& mv, int sms, con
         cudaMemsetAsync(prefix->slots, 0xFF, (size_t)max_rows * k3::kPrefixEvals * 6 * sizeof(double), st);   // NaN = empty
         const int pblocks = (max_rows + 127) / 128;
         if (fast_rcp) {
-            k3::prefix_table_kernel<JXB_P, true><<<1, 128, 0, st>>>(mv, sp, (const k3::LogTable*)log_table, *prefix);
+            if (build_tables) k3::prefix_table_kernel<JXB_P, true><<<1, 128, 0, st>>>(mv, sp, (const k3::LogTable*)log_table, *prefix);
             k3::prefix_eval_kernel<JXB_P, true><<<pblocks, 128, kSmemPrefix, st>>>(mv, *prefix, rot, ldc, max_rows, n_rows_dev, sp, ssq);
         } else {
-            k3::prefix_table_kernel<JXB_P, false><<<1, 128, 0, st>>>(mv, sp, (const k3::LogTable*)log_table, *prefix);
+            if (build_tables) k3::prefix_table_kernel<JXB_P, false><<<1, 128, 0, st>>>(mv, sp, (const k3::LogTable*)log_table, *prefix);
             k3::prefix_eval_kernel<JXB_P, false><<<pblocks, 128, kSmemPrefix, st>>>(mv, *prefix, rot, ldc, max_rows, n_rows_dev, sp, ssq);
         }
     }

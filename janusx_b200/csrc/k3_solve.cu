@@ -3,6 +3,7 @@
 #include "k3_solve.cuh"
 
 #include <cmath>
+#include <cstring>
 
 namespace jxb {
 
@@ -16,7 +17,7 @@ namespace jxb {
                                     const SolveParams&, double*, int, int32_t*, const void*, cudaStream_t);    \
     int k3_launch_solve_lane_p##P(const k3::ModelView&, int, const float*, size_t, int, const int32_t*,        \
                                   const SolveParams&, double*, int, int32_t*, const void*, double*, int32_t*,  \
-                                  int, const k3::PrefixTables*, cudaStream_t);                                 \
+                                  int, const k3::PrefixTables*, int, cudaStream_t);                            \
     int k3_prefix_table_doubles_p##P();                                                                        \
     int k3_prefix_rec_doubles_p##P();                                                                          \
     int k3_launch_solve_lane_stream_p##P(const k3::ModelView&, int, const float*, size_t, int, const SolveParams&, \
@@ -166,6 +167,7 @@ int launch_solve_lane(Model& m, const float* rot, size_t ldc, size_t max_rows, c
     // shared-abscissa prefix (k3_solve.cuh prefix_eval_kernel): one allocation {xs[8] | sums | rec[n_pad][rsf] | slots}
     PrefixTables pt{};
     const PrefixTables* prefix = nullptr;
+    int build_tables = 0;
     // (7 and 8 covariate columns: four abscissae x (p + 2) running sums no longer fit the register file; plain searches)
     if (m.p <= 6 && (g_prefix_evals == 2 || (g_prefix_evals && max_rows >= g_prefix_min_rows))) {
         const size_t n_pad = (m.n + 31) & ~(size_t)31;
@@ -181,7 +183,7 @@ int launch_solve_lane(Model& m, const float* rot, size_t ldc, size_t max_rows, c
         if (m.prefix_cap < need) {
             JXB_CUDA_OK(cudaStreamSynchronize(st));
             if (m.prefix_buf) cudaFree(m.prefix_buf);
-            m.prefix_buf = nullptr; m.prefix_cap = 0;
+            m.prefix_buf = nullptr; m.prefix_cap = 0; m.prefix_valid = false;
             JXB_CUDA_OK(cudaMalloc((void**)&m.prefix_buf, need * sizeof(double)));
             m.prefix_cap = need;
         }
@@ -190,9 +192,14 @@ int launch_solve_lane(Model& m, const float* rot, size_t ldc, size_t max_rows, c
         pt.rec = m.prefix_buf + head;
         pt.slots = pt.rec + n_pad * rsf;
         prefix = &pt;
-        note_launch(2);   // prefix_table_kernel + prefix_eval_kernel
+        // the tables depend on the model and the search set-up only, not on the batch
+        const double key[7] = {sp.low, sp.high, sp.tol, (double)sp.max_iter, (double)(sp.has_init != 0),
+                               sp.has_init ? sp.init : 0.0, (double)fast};
+        build_tables = !m.prefix_valid || memcmp(key, m.prefix_key, sizeof(key)) != 0;
+        if (build_tables) { memcpy(m.prefix_key, key, sizeof(key)); m.prefix_valid = true; }
+        note_launch(build_tables ? 2 : 1);   // [prefix_table_kernel +] prefix_eval_kernel
     }
-#define L_STATIC(P) k3_launch_solve_lane_p##P(mv, sms, rot, ldc, (int)max_rows, n_rows_dev, sp, out, out_cols, evals, m.log_table, m.ssq, queue, fast, prefix, st)
+#define L_STATIC(P) k3_launch_solve_lane_p##P(mv, sms, rot, ldc, (int)max_rows, n_rows_dev, sp, out, out_cols, evals, m.log_table, m.ssq, queue, fast, prefix, build_tables, st)
 #define L_DYN() (void)0
     JXB_DISPATCH_P((int)m.p, L_STATIC, L_DYN)
 #undef L_STATIC

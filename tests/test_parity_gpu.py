@@ -541,9 +541,20 @@ def test_shared_abscissa_prefix_matches_plain_search(jx, oracle, p_cov):
             for v in variants:
                 jx.set_prefix_evals(2)
                 a = mdl.scan_packed(case.packed, n, **v)
+                a2 = mdl.scan_packed(case.packed, n, **v)           # second batch of the same search set-up: cached tables
                 jx.set_prefix_evals(0)
                 b = mdl.scan_packed(case.packed, n, **v)
                 assert np.array_equal(a[3], b[3], equal_nan=True) and np.array_equal(a[4], b[4]), (divide, v)
+                assert np.array_equal(a[3], a2[3], equal_nan=True) and np.array_equal(a[4], a2[4]), (divide, v)
+        # a new phenotype on the same model invalidates the tables
+        jx.set_prefix_evals(2)
+        y2 = nm["y"] * 1.5 + 0.25
+        mdl.set_xy(nm["xcov"], y2)
+        a = mdl.scan_packed(case.packed, n, **kw2)
+        jx.set_prefix_evals(0)
+        b = mdl.scan_packed(case.packed, n, **kw2)
+        assert np.array_equal(a[3], b[3], equal_nan=True) and np.array_equal(a[4], b[4])
+        assert not np.array_equal(a[3], out, equal_nan=True)
     finally:
         jx._cabi.lib().jxb_set_generic_divide(0)
         jx.set_prefix_evals(1)
