@@ -913,3 +913,13 @@ def test_cli_lm_switch_without_force_model(jx, tmp_path, capsys):
     assert rc == 3 and "switch to LM for trait noise" in err and not (tmp_path / "out" / "r.noise.lmm.tsv").exists()
     rc = gwas.main(common + ["-force-model"])
     assert rc == 0 and (tmp_path / "out" / "r.noise.lmm.tsv").exists()
+
+
+def test_graft_entry_smoke():
+    """`__graft_entry__.smoke()` (what the driver runs before the bench): both kernel sets against the oracle."""
+    import importlib
+    import sys
+    root = str(__import__("pathlib").Path(__file__).resolve().parents[1])
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    importlib.import_module("__graft_entry__").smoke()
