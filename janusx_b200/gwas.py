@@ -250,10 +250,16 @@ def main(argv: Optional[List[str]] = None) -> int:
                 X_parts.append(np.stack([cov_mat[pos_cov[s]] for s in sample_ids]))
             t_null = time.time()
             if nq > 0:
+                # the PCs and the null model take the same decomposition: K + 1e-6 I is the matrix LMM() itself decomposes
+                # (pyBLUP/assoc.py:1626-1629), so it is decomposed once and handed over (LMM.from_spectral, assoc.py:1726)
                 evals, evecs = assoc._eigh(K + 1e-6 * np.eye(n), device)
+                evd_s = time.time() - t_null
                 X_parts.append(evecs[:, ::-1][:, :nq] * np.sqrt(np.maximum(evals[::-1][:nq], 0.0)))
-            X_cov = np.concatenate(X_parts, axis=1) if X_parts else None
-            base = assoc.LMM(y, X_cov, K, device=device)
+                X_cov = np.concatenate(X_parts, axis=1)
+                base = assoc.LMM.from_spectral(y, X_cov, evals, evecs, evd_secs=evd_s, device=device)
+            else:
+                X_cov = np.concatenate(X_parts, axis=1) if X_parts else None
+                base = assoc.LMM(y, X_cov, K, device=device)
             l10 = float(np.log10(base.lbd_null))
             log(f"[{trait}] n={n} covariates={base.Xcov.shape[1]} lambda_null={base.lbd_null:.6g} "
                 f"pve={base.pve:.4f} bounds=({base.bounds[0]:.3f},{base.bounds[1]:.3f}) null model {time.time() - t_null:.2f} s")
