@@ -7,8 +7,11 @@ The per-row QC of this route is NOT the unified scan's f32 arithmetic: it runs i
 (process_snp_row_with_precomputed_counts_impl, src/io/gfcore.rs:405-480).  The counts are exact integers, so they come
 from the device (jxb_decode_packed), the handful of f64 expressions per row is evaluated here exactly as the reference
 writes them, and the decode / impute / centre of the kept rows runs on the device (jxb_decode_packed_prepared).
-Not built: bim_range / snp_sites / chr_keys / bp_min / bp_max / ranges selectors, the windowed mmap, fill_missing = False,
-non-additive codings (their value map applies a 1e-6 tolerance to the imputed dosage, src/io/gfreader.rs:3161-3186).
+Row selection (snp_range / snp_indices / bim_range / snp_sites, then the chr_keys / bp_min / bp_max / ranges site filter)
+is host logic and follows src/io/gfreader.rs:125-215, 583-726, 3256-3281 (`select_snp_rows`).  `mmap_window_mb` is
+accepted with the reference's argument check; the payload is a demand-paged numpy memmap either way.
+Not built: fill_missing = False, non-additive codings (their value map applies a 1e-6 tolerance to the imputed dosage,
+src/io/gfreader.rs:3161-3186).
 """
 from __future__ import annotations
 
@@ -28,6 +31,104 @@ class ChunkSite(SiteInfo):
     def __init__(self, chrom, pos, snp, ref_allele, alt_allele):
         super().__init__(chrom, pos, ref_allele, alt_allele)
         self.snp = str(snp)
+
+
+def normalize_chr_key(chrom: str) -> str:
+    """Chromosome key of the site filter (src/io/gfreader.rs:227-234): trimmed, a leading "chr" (any case) dropped, upper case."""
+    c = str(chrom).strip()
+    if c[:3].lower() == "chr":
+        c = c[3:]
+    return c.strip().upper()
+
+
+def select_snp_rows(chroms: Sequence[str], positions: Sequence[int], snp_range=None, snp_indices=None, bim_range=None,
+                    snp_sites=None, chr_keys=None, bp_min=None, bp_max=None, ranges=None) -> Optional[np.ndarray]:
+    """Source rows a BedChunkReader walks, in order; None = every row of the BIM.
+
+    First one of the four primary selectors (src/io/gfreader.rs:125-215: at most one; snp_range half open; snp_indices as
+    given, in range, no duplicates; bim_range by exact chromosome string and closed position interval; snp_sites in the order
+    of the keys, every key must exist, a key listed twice in the BIM contributes all its rows), then the site filter on what is
+    left (src/io/gfreader.rs:583-726, 3259-3281: normalised chromosome keys, every given condition must hold, `ranges` is
+    a union).  Errors carry the reference's messages (RuntimeError there as here)."""
+    m = len(chroms)
+    if sum(v is not None for v in (snp_range, snp_indices, bim_range, snp_sites)) > 1:
+        raise RuntimeError("Provide only one of snp_range, snp_indices, bim_range, or snp_sites")
+    pos = np.asarray(positions, dtype=np.int64)
+    rows: Optional[np.ndarray] = None
+    if snp_range is not None:
+        start, end = int(snp_range[0]), int(snp_range[1])
+        if start >= end or end > m:
+            raise RuntimeError(f"invalid snp_range: ({start}, {end})")
+        rows = np.arange(start, end, dtype=np.int64)
+    elif snp_indices is not None:
+        rows = np.asarray(list(snp_indices), dtype=np.int64)
+        if rows.size == 0:
+            raise RuntimeError("snp_indices is empty")
+        seen = set()
+        for i in rows.tolist():
+            if i < 0 or i >= m:
+                raise RuntimeError(f"snp index out of range: {i}")
+            if i in seen:
+                raise RuntimeError(f"duplicate snp index: {i}")
+            seen.add(i)
+    elif bim_range is not None:
+        chrom, start, end = str(bim_range[0]), int(bim_range[1]), int(bim_range[2])
+        if start > end:
+            raise RuntimeError("bim_range start > end")
+        same = np.fromiter((c == chrom for c in chroms), dtype=bool, count=m)
+        rows = np.nonzero(same & (pos >= start) & (pos <= end))[0].astype(np.int64)
+    elif snp_sites is not None:
+        keys = [(str(c), int(p)) for c, p in snp_sites]
+        if not keys:
+            raise RuntimeError("snp_sites is empty")
+        where = {}
+        for i, (c, p) in enumerate(zip(chroms, pos.tolist())):
+            where.setdefault((c, p), []).append(i)
+        picked: List[int] = []
+        for c, p in keys:
+            if (c, p) not in where:
+                raise RuntimeError(f"snp site not found: ({c}, {p})")
+            picked.extend(where[(c, p)])
+        if not picked:
+            raise RuntimeError("no SNPs matched from snp_sites")
+        rows = np.asarray(picked, dtype=np.int64)
+
+    # site filter
+    if bp_min is not None and bp_max is not None and int(bp_min) > int(bp_max):
+        raise RuntimeError("bp_min cannot be greater than bp_max")
+    chr_set = None
+    if chr_keys is not None:
+        chr_set = {k for k in (normalize_chr_key(c) for c in chr_keys) if k}
+        chr_set = chr_set or None
+    rng = None
+    if ranges is not None and len(ranges) > 0:
+        rng = []
+        for c, a, b in ranges:
+            if int(a) > int(b):
+                raise RuntimeError("One range has start > end")
+            rng.append((normalize_chr_key(c), int(a), int(b)))
+    if chr_set is None and bp_min is None and bp_max is None and rng is None:
+        return rows
+    cand = np.arange(m, dtype=np.int64) if rows is None else rows
+    norm = {}
+    keep = np.ones(cand.shape[0], dtype=bool)
+    for j, i in enumerate(cand.tolist()):
+        c = chroms[i]
+        k = norm.get(c)
+        if k is None:
+            k = norm[c] = normalize_chr_key(c)
+        p = int(pos[i])
+        ok = True
+        if chr_set is not None and k not in chr_set:
+            ok = False
+        if ok and bp_min is not None and p < int(bp_min):
+            ok = False
+        if ok and bp_max is not None and p > int(bp_max):
+            ok = False
+        if ok and rng is not None and not any(k == rc and rs <= p <= re for rc, rs, re in rng):
+            ok = False
+        keep[j] = ok
+    return cand[keep]
 
 
 def _simple_allele(a: str) -> bool:
@@ -107,10 +208,8 @@ class BedChunkReader:
         self.het = 1.0 if het_threshold is None else float(het_threshold)
         if not (0.0 <= self.het <= 1.0):
             raise ValueError("het_threshold must be within [0, 1.0]")
-        for name, v in (("bim_range", bim_range), ("snp_sites", snp_sites), ("mmap_window_mb", mmap_window_mb),
-                        ("chr_keys", chr_keys), ("bp_min", bp_min), ("bp_max", bp_max), ("ranges", ranges)):
-            if v is not None:
-                raise NotImplementedError(f"BedChunkReader({name}=...) is not built in janusx_b200")
+        if mmap_window_mb is not None and (snp_range is not None or snp_indices is not None or bim_range is not None):
+            raise ValueError("mmap_window_mb does not support snp_range/snp_indices/bim_range")   # gfreader.rs:3246-3252
         self.prefix = str(prefix)
         with open(self.prefix + ".fam") as fh:
             fam = [line.split()[1] for line in fh if line.strip()]
@@ -170,24 +269,10 @@ class BedChunkReader:
         if (raw.shape[0] - 3) % bps != 0 or (raw.shape[0] - 3) // bps != len(self._sites):
             raise RuntimeError("BED payload does not match the FAM/BIM dimensions")
         self._packed = raw[3:].reshape(len(self._sites), bps)
-        # build_snp_indices, src/io/gfreader.rs:125-172 (snp_range / snp_indices only)
-        if snp_range is not None and snp_indices is not None:
-            raise RuntimeError("Provide only one of snp_range, snp_indices, bim_range, or snp_sites")
-        self._snp_indices: Optional[np.ndarray] = None
-        if snp_range is not None:
-            start, end = int(snp_range[0]), int(snp_range[1])
-            if start >= end or end > len(self._sites):
-                raise RuntimeError(f"invalid snp_range: ({start}, {end})")
-            self._snp_indices = np.arange(start, end, dtype=np.int64)
-        elif snp_indices is not None:
-            si = np.asarray(list(snp_indices), dtype=np.int64)
-            if si.size == 0:
-                raise RuntimeError("snp_indices is empty")
-            if si.min() < 0 or si.max() >= len(self._sites):
-                raise RuntimeError(f"snp index out of range: {int(si.max() if si.max() >= len(self._sites) else si.min())}")
-            if np.unique(si).size != si.size:
-                raise RuntimeError("duplicate snp index")
-            self._snp_indices = si
+        # build_snp_indices + the site filter, src/io/gfreader.rs:125-215, 3256-3281
+        self._snp_indices: Optional[np.ndarray] = select_snp_rows(
+            [st.chrom for st in self._sites], [st.pos for st in self._sites], snp_range=snp_range, snp_indices=snp_indices,
+            bim_range=bim_range, snp_sites=snp_sites, chr_keys=chr_keys, bp_min=bp_min, bp_max=bp_max, ranges=ranges)
         self._cursor = 0
         n = len(idx)
         self._dev = DeviceModel(np.ones(n), np.ones((n, 1)), np.zeros(n), device=device)   # decode workspace only

@@ -233,3 +233,52 @@ def test_raw_next_chunk_minor_allele_recoding(jx, oracle, tmp_path):
             assert alleles[len(want_rows) - 1] == ("T", "A")
     assert names == want_names and flips > 20
     assert np.array_equal(g.view(np.uint32), np.stack(want_rows).view(np.uint32))
+
+
+def test_reader_site_selectors(jx, oracle, tmp_path):
+    """bim_range / snp_sites / chr_keys / bp_min / bp_max / ranges (src/io/gfreader.rs:125-215, 583-726, 3246-3281): the
+    reader walks exactly the rows the same selection given as snp_indices walks, bit for bit."""
+    from janusx_b200 import synth
+    from janusx_b200.gfreader import BedChunkReader
+    n_full, m = 97, 420
+    packed, _ = synth.draw_genotypes(m, n_full, seed=23, missing_rate=0.03)
+    prefix = str(tmp_path / "sel")
+    synth.write_plink(prefix, packed, n_full)
+    # three chromosomes, one written with a "chr" prefix
+    lines = open(prefix + ".bim").read().splitlines()
+    with open(prefix + ".bim", "w") as fh:
+        for i, ln in enumerate(lines):
+            tok = ln.split("\t")
+            tok[0] = ("1", "chr2", "X")[i // 140]
+            tok[3] = str(1000 + 10 * (i % 140))
+            fh.write("\t".join(tok) + "\n")
+
+    def rows_of(**kw):
+        rd = BedChunkReader(prefix, maf_threshold=0.0, max_missing_rate=1.0, **kw)
+        if rd.n_snps == 0:
+            assert rd.next_chunk_prepared(64) is None
+            return 0, None, []
+        g, sites, af, miss, _ = _read_all(rd, 64)
+        return rd.n_snps, g, [(s.chrom, s.pos, s.snp) for s in sites]
+
+    cases = [
+        (dict(bim_range=("chr2", 1100, 1500)), list(range(150, 191))),
+        (dict(bim_range=("2", 1100, 1500)), []),                                   # exact chromosome string
+        (dict(snp_sites=[("X", 1000), ("1", 1050), ("chr2", 2390)]), [280, 5, 279]),
+        (dict(chr_keys=["2"]), list(range(140, 280))),                             # normalised on both sides
+        (dict(chr_keys=["CHRX", "1"], bp_min=2300), list(range(130, 140)) + list(range(410, 420))),
+        (dict(ranges=[("chr1", 1000, 1040), ("x", 2380, 2390)], bp_max=2385), [0, 1, 2, 3, 4, 418]),
+        (dict(snp_range=(100, 200), chr_keys=["chr2"], bp_max=1100), list(range(140, 151))),
+    ]
+    for kw, want in cases:
+        n_snps, g, sites = rows_of(**kw)
+        assert n_snps == len(want), kw
+        if not want:
+            continue
+        n2, g2, sites2 = rows_of(snp_indices=want)
+        assert sites == sites2 and np.array_equal(g.view(np.uint32), g2.view(np.uint32)), kw
+    with pytest.raises(ValueError, match="mmap_window_mb does not support"):
+        BedChunkReader(prefix, mmap_window_mb=64, snp_range=(0, 10))
+    assert BedChunkReader(prefix, mmap_window_mb=64, chr_keys=["X"]).n_snps == 140
+    with pytest.raises(RuntimeError, match="snp site not found"):
+        BedChunkReader(prefix, snp_sites=[("1", 7)])

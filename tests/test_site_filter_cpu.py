@@ -1,0 +1,58 @@
+"""Row selection of BedChunkReader (host logic, src/io/gfreader.rs:125-215, 583-726, 3246-3281): the four primary
+selectors, the site filter applied on top, the reference's error messages."""
+import numpy as np
+import pytest
+
+from janusx_b200.gfreader import normalize_chr_key, select_snp_rows
+
+CHROMS = ["1", "1", "chr2", "2", "X", "1", " Chr3 ", "3"]
+POS = [10, 20, 5, 30, 7, 20, 11, 12]
+
+
+def test_chr_key_normalisation():
+    assert normalize_chr_key("chr1") == "1" and normalize_chr_key(" CHRx ") == "X" and normalize_chr_key("Chr 7") == "7"
+    assert normalize_chr_key("mt") == "MT" and normalize_chr_key("") == "" and normalize_chr_key("ch1") == "CH1"
+
+
+def test_primary_selectors():
+    assert select_snp_rows(CHROMS, POS) is None
+    assert select_snp_rows(CHROMS, POS, snp_range=(1, 4)).tolist() == [1, 2, 3]
+    assert select_snp_rows(CHROMS, POS, snp_indices=[5, 0, 7]).tolist() == [5, 0, 7]          # order kept
+    assert select_snp_rows(CHROMS, POS, bim_range=("1", 10, 20)).tolist() == [0, 1, 5]         # closed interval
+    assert select_snp_rows(CHROMS, POS, bim_range=("2", 0, 100)).tolist() == [3]               # exact chromosome string
+    assert select_snp_rows(CHROMS, POS, bim_range=("9", 0, 100)).tolist() == []                # empty selection is allowed
+    assert select_snp_rows(CHROMS, POS, snp_sites=[("1", 20), ("X", 7)]).tolist() == [1, 5, 4]  # key order, duplicates of a key
+
+
+@pytest.mark.parametrize("kw, msg", [
+    (dict(snp_range=(0, 2), snp_indices=[1]), "Provide only one of snp_range, snp_indices, bim_range, or snp_sites"),
+    (dict(bim_range=("1", 0, 5), snp_sites=[("1", 10)]), "Provide only one of"),
+    (dict(snp_range=(3, 3)), r"invalid snp_range: \(3, 3\)"),
+    (dict(snp_range=(0, 9)), r"invalid snp_range: \(0, 9\)"),
+    (dict(snp_indices=[]), "snp_indices is empty"),
+    (dict(snp_indices=[8]), "snp index out of range: 8"),
+    (dict(snp_indices=[2, 2]), "duplicate snp index: 2"),
+    (dict(bim_range=("1", 5, 4)), "bim_range start > end"),
+    (dict(snp_sites=[]), "snp_sites is empty"),
+    (dict(snp_sites=[("1", 11)]), r"snp site not found: \(1, 11\)"),
+    (dict(bp_min=9, bp_max=8), "bp_min cannot be greater than bp_max"),
+    (dict(ranges=[("1", 9, 8)]), "One range has start > end"),
+])
+def test_selector_errors(kw, msg):
+    with pytest.raises(RuntimeError, match=msg):
+        select_snp_rows(CHROMS, POS, **kw)
+
+
+def test_site_filter_on_top():
+    # every given condition must hold; chromosome keys are normalised on both sides
+    assert select_snp_rows(CHROMS, POS, chr_keys=["CHR2"]).tolist() == [2, 3]
+    assert select_snp_rows(CHROMS, POS, chr_keys=["chr2", "3"], bp_min=6).tolist() == [3, 6, 7]
+    assert select_snp_rows(CHROMS, POS, bp_min=10, bp_max=12).tolist() == [0, 6, 7]
+    assert select_snp_rows(CHROMS, POS, ranges=[("chr1", 15, 25), ("x", 0, 10)]).tolist() == [1, 4, 5]   # union of ranges
+    assert select_snp_rows(CHROMS, POS, ranges=[("1", 0, 100)], chr_keys=["2"]).tolist() == []
+    # applied to what the primary selector left, order kept
+    assert select_snp_rows(CHROMS, POS, snp_indices=[5, 4, 0], ranges=[("chr1", 15, 25), ("x", 0, 10)]).tolist() == [5, 4]
+    assert select_snp_rows(CHROMS, POS, snp_range=(0, 6), chr_keys=["1"], bp_max=10).tolist() == [0]
+    # empty key lists / range lists switch their condition off
+    assert select_snp_rows(CHROMS, POS, chr_keys=[" "], ranges=[]) is None
+    assert select_snp_rows(CHROMS, POS, snp_range=(2, 4), chr_keys=[]).tolist() == [2, 3]
