@@ -10,8 +10,8 @@ writes them, and the decode / impute / centre of the kept rows runs on the devic
 Row selection (snp_range / snp_indices / bim_range / snp_sites, then the chr_keys / bp_min / bp_max / ranges site filter)
 is host logic and follows src/io/gfreader.rs:125-215, 583-726, 3256-3281 (`select_snp_rows`).  `mmap_window_mb` is
 accepted with the reference's argument check; the payload is a demand-paged numpy memmap either way.
-Not built: fill_missing = False, non-additive codings (their value map applies a 1e-6 tolerance to the imputed dosage,
-src/io/gfreader.rs:3161-3186).
+Non-additive codings of next_chunk_prepared (dom / rec / het, src/io/gfreader.rs:3161-3186): four values per row computed
+here exactly as the reference writes them, per-row LUT decode on the device.  Not built: fill_missing = False.
 """
 from __future__ import annotations
 
@@ -192,6 +192,29 @@ def raw_row_decisions(missing, het, hom_alt, n: int, maf_thr: float, miss_thr: f
     return keep, flip, lut
 
 
+def coded_row_lut(missing, het, hom_alt, imputed, n: int, coding: str):
+    """Non-additive codings of next_chunk_prepared (src/io/gfreader.rs:3161-3186, 3632-3653) for rows whose missing calls
+    were filled with `imputed`: value map with the reference's 1e-6 tolerance in f32, exact sum of the coded row, mean as
+    f32(sum / n), centring in f32 -> (lut f32[m, 4] indexed by the PLINK 2-bit code {hom-ref, missing, het, hom-alt},
+    coded_mean f32[m])."""
+    missing = np.asarray(missing, dtype=np.int64)
+    het = np.asarray(het, dtype=np.int64)
+    hom = np.asarray(hom_alt, dtype=np.int64)
+    imputed = np.asarray(imputed, dtype=np.float32)
+    m = missing.shape[0]
+    vals = np.empty((m, 4), dtype=np.float32)
+    vals[:, 0] = np.float32(0.0); vals[:, 1] = imputed; vals[:, 2] = np.float32(1.0); vals[:, 3] = np.float32(2.0)
+    tol = np.float32(1e-6)
+    near1 = np.abs(vals - np.float32(1.0)) <= tol
+    near2 = np.abs(vals - np.float32(2.0)) <= tol
+    hit = {"dom": near1 | near2, "rec": near2, "het": near1}[coding]
+    coded = np.where(hit, np.float32(1.0), np.float32(0.0)).astype(np.float32)
+    cnt = np.stack([n - missing - het - hom, missing, het, hom], axis=1).astype(np.float64)
+    total = (cnt * coded.astype(np.float64)).sum(axis=1)                 # 0/1 values times counts: an exact integer
+    coded_mean = (total / float(n)).astype(np.float32)
+    return np.ascontiguousarray(coded - coded_mean[:, None], dtype=np.float32), coded_mean
+
+
 class BedChunkReader:
     def __init__(self, prefix, maf_threshold=None, max_missing_rate=None, fill_missing=None, snp_range=None,
                  snp_indices=None, bim_range=None, snp_sites=None, sample_ids=None, sample_indices=None,
@@ -210,6 +233,7 @@ class BedChunkReader:
             raise ValueError("het_threshold must be within [0, 1.0]")
         if mmap_window_mb is not None and (snp_range is not None or snp_indices is not None or bim_range is not None):
             raise ValueError("mmap_window_mb does not support snp_range/snp_indices/bim_range")   # gfreader.rs:3246-3252
+        self._mmap_window_mb = mmap_window_mb
         self.prefix = str(prefix)
         with open(self.prefix + ".fam") as fh:
             fam = [line.split()[1] for line in fh if line.strip()]
@@ -340,8 +364,8 @@ class BedChunkReader:
         coding_key = (coding or "add").strip().lower()
         if coding_key not in ("add", "dom", "rec", "het"):
             raise ValueError("coding must be one of: add, dom, rec, het")
-        if coding_key != "add":
-            raise NotImplementedError("next_chunk_prepared: only the additive coding is built in janusx_b200")
+        if self._mmap_window_mb is not None and self._snp_indices is not None:   # gfreader.rs:3687-3692
+            raise RuntimeError("windowed mmap mode does not support explicit snp index selection")
         n = self.n_samples
         sidx = None if self._identity else self._sidx
         blocks, sites, afs, misses, m = [], [], [], [], 0
@@ -355,6 +379,17 @@ class BedChunkReader:
                                   for r in rows], dtype=bool)
             nk = int(keep.sum())
             if nk == 0:
+                continue
+            if coding_key != "add":
+                # dom / rec / het: the filled row takes four values {0, imputed, 1, 2}; the coding map, the exact f64 sum of
+                # the coded row and the f32 centring give four output values per row -> per-row LUT decode on the device
+                k = np.nonzero(keep)[0]
+                lut, coded_mean = coded_row_lut(counts[k, 0], counts[k, 1], counts[k, 2], imputed[k], n, coding_key)
+                blocks.append(self._decode_lut(np.ascontiguousarray(packed[k]), lut))
+                sites.extend(self._sites[int(rows[i])] for i in k)
+                afs.append(coded_mean)
+                misses.append(counts[k, 0].astype(np.float32))
+                m += nk
                 continue
             g = np.empty((nk, n), dtype=np.float32)
             got = C.c_size_t()

@@ -282,3 +282,39 @@ def test_reader_site_selectors(jx, oracle, tmp_path):
     assert BedChunkReader(prefix, mmap_window_mb=64, chr_keys=["X"]).n_snps == 140
     with pytest.raises(RuntimeError, match="snp site not found"):
         BedChunkReader(prefix, snp_sites=[("1", 7)])
+
+
+@pytest.mark.parametrize("coding", ["dom", "rec", "het"])
+def test_prepared_chunks_non_additive_codings(jx, oracle, tmp_path, coding):
+    """next_chunk_prepared(coding=dom|rec|het) (src/io/gfreader.rs:3161-3186, 3632-3653): rows, af (= coded mean) and missing
+    counts against the per-sample restatement, on all samples and on a subset, independent of the chunk size."""
+    from janusx_b200 import synth
+    from janusx_b200.gfreader import BedChunkReader
+    n_full, m = 83, 300
+    packed, _ = synth.draw_genotypes(m, n_full, seed=31, missing_rate=0.05)
+    prefix = str(tmp_path / "cod")
+    synth.write_plink(prefix, packed, n_full)
+    fam = oracle.read_fam(prefix)
+    sub = sorted(np.random.default_rng(3).choice(n_full, size=60, replace=False).tolist())
+    for kw, cols in ((dict(), list(range(n_full))), (dict(sample_ids=[fam[i] for i in sub]), sub)):
+        n = len(cols)
+        codes = np.stack([(packed[:, j // 4] >> ((j % 4) * 2)) & 3 for j in cols], axis=1)
+        rd = BedChunkReader(prefix, maf_threshold=0.02, max_missing_rate=0.2, **kw)
+        g, sites, af, miss, _ = _read_all(rd, 77, coding=coding)
+        g_big = _read_all(BedChunkReader(prefix, maf_threshold=0.02, max_missing_rate=0.2, **kw), 10_000, coding=coding)[0]
+        assert np.array_equal(g.view(np.uint32), g_big.view(np.uint32))
+        keep, _, _, _ = oracle.bed_chunk_prepared_rows(packed, n_full, None if not kw else np.asarray(sub, dtype=np.int64),
+                                                       0.02, 0.2, 1.0)
+        kept = np.nonzero(keep)[0]
+        assert g.shape == (kept.size, n) and [s.snp for s in sites] == [f"snp{i}" for i in kept]
+        one, two, tol = np.float32(1.0), np.float32(2.0), np.float32(1e-6)
+        for out_r, i in enumerate(kept):
+            c = codes[i]
+            nm = c != 1
+            imputed = np.float32(float((c == 2).sum() + 2 * (c == 3).sum()) / float(nm.sum()))
+            filled = np.array([0.0, imputed, 1.0, 2.0], dtype=np.float32)[c]
+            h1, h2 = np.abs(filled - one) <= tol, np.abs(filled - two) <= tol
+            coded = np.where({"dom": h1 | h2, "rec": h2, "het": h1}[coding], one, np.float32(0.0)).astype(np.float32)
+            cm = np.float32(float(coded.astype(np.float64).sum()) / n)
+            assert np.array_equal(g[out_r].view(np.uint32), (coded - cm).view(np.uint32)), (coding, i)
+            assert af[out_r].view(np.uint32) == cm.view(np.uint32) and miss[out_r] == float((c == 1).sum())

@@ -56,3 +56,33 @@ def test_site_filter_on_top():
     # empty key lists / range lists switch their condition off
     assert select_snp_rows(CHROMS, POS, chr_keys=[" "], ranges=[]) is None
     assert select_snp_rows(CHROMS, POS, snp_range=(2, 4), chr_keys=[]).tolist() == [2, 3]
+
+
+@pytest.mark.parametrize("coding", ["dom", "rec", "het"])
+def test_coded_row_lut_equals_row_by_row_restatement(coding):
+    """Non-additive codings of next_chunk_prepared (src/io/gfreader.rs:3161-3186, 3632-3653): the four values per row
+    against the reference's per-sample loop (map with 1e-6 tolerance, f64 sum, f32 mean, f32 centring)."""
+    from janusx_b200.gfreader import coded_row_lut, prepared_row_decisions
+    rng = np.random.default_rng(5)
+    n = 37
+    rows = [rng.choice(4, size=n, p=[0.5, 0.1, 0.3, 0.1]) for _ in range(40)]
+    rows.append(np.array([2] * 30 + [1] * 7))          # every call het or missing: imputed == 1.0 exactly
+    rows.append(np.array([3] * 30 + [1] * 7))          # every call hom-alt or missing: imputed == 2.0 exactly
+    rows.append(np.array([2] * 18 + [3] * 18 + [1]))   # imputed 1.5
+    codes = np.stack(rows)
+    missing, het, hom = (codes == 1).sum(1), (codes == 2).sum(1), (codes == 3).sum(1)
+    keep, imputed = prepared_row_decisions(missing, het, hom, n, 0.0, 1.0, 1.0)
+    lut, mean = coded_row_lut(missing, het, hom, imputed, n, coding)
+    one, two, tol = np.float32(1.0), np.float32(2.0), np.float32(1e-6)
+    for r in range(codes.shape[0]):
+        filled = np.array([0.0, imputed[r], 1.0, 2.0], dtype=np.float32)[codes[r]]
+        total, coded = 0.0, np.empty(n, dtype=np.float32)
+        for j, v in enumerate(filled):
+            h1, h2 = abs(np.float32(v - one)) <= tol, abs(np.float32(v - two)) <= tol
+            mv = np.float32(1.0 if {"dom": h1 or h2, "rec": h2, "het": h1}[coding] else 0.0)
+            coded[j] = mv
+            total += float(mv)
+        cm = np.float32(total / n)
+        want = coded - cm
+        assert mean[r].view(np.uint32) == cm.view(np.uint32)
+        assert np.array_equal(lut[r][codes[r]].view(np.uint32), want.view(np.uint32)), (coding, r)
