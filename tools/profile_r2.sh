@@ -5,7 +5,7 @@
 set -u
 mkdir -p gpurun_out
 BENCH="python bench.py --scaling weak --steps 1 --warmup 1 --e2e-steps 1 --no-cpu-baseline"
-K='regex:i8_rotate_kernel|solve_lane_kernel|decode_int8_kernel|row_ssq_kernel|compact_kernel'
+K='regex:i8_rotate_kernel|solve_lane_kernel|prefix_|decode_int8_kernel|row_ssq_kernel|compact_kernel'
 timeout 240 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum,sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_fp64.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed,l1tex__t_sector_hit_rate.pct,lts__t_sector_hit_rate.pct,smsp__warps_active.avg.per_cycle_active,launch__registers_per_thread,dram__throughput.avg.pct_of_peak_sustained_elapsed \
     --clock-control none -k "$K" -c 12 --csv --log-file gpurun_out/r2_ncu_metrics.csv $BENCH > gpurun_out/r2_ncu_metrics.out 2>&1
 echo "ncu metrics rc=$?"
