@@ -11,7 +11,8 @@ Row selection (snp_range / snp_indices / bim_range / snp_sites, then the chr_key
 is host logic and follows src/io/gfreader.rs:125-215, 583-726, 3256-3281 (`select_snp_rows`).  `mmap_window_mb` is
 accepted with the reference's argument check; the payload is a demand-paged numpy memmap either way.
 Non-additive codings of next_chunk_prepared (dom / rec / het, src/io/gfreader.rs:3161-3186): four values per row computed
-here exactly as the reference writes them, per-row LUT decode on the device.  Not built: fill_missing = False.
+here exactly as the reference writes them, per-row LUT decode on the device; fill_missing = false (missing calls keep the
+decoder's -9 marker, src/io/gfcore.rs:468-476) goes the same way.
 """
 from __future__ import annotations
 
@@ -193,10 +194,11 @@ def raw_row_decisions(missing, het, hom_alt, n: int, maf_thr: float, miss_thr: f
 
 
 def coded_row_lut(missing, het, hom_alt, imputed, n: int, coding: str):
-    """Non-additive codings of next_chunk_prepared (src/io/gfreader.rs:3161-3186, 3632-3653) for rows whose missing calls
-    were filled with `imputed`: value map with the reference's 1e-6 tolerance in f32, exact sum of the coded row, mean as
-    f32(sum / n), centring in f32 -> (lut f32[m, 4] indexed by the PLINK 2-bit code {hom-ref, missing, het, hom-alt},
-    coded_mean f32[m])."""
+    """Codings of next_chunk_prepared (src/io/gfreader.rs:3161-3186, 3632-3653) for rows whose missing calls hold
+    `imputed` (the row mean, or the raw marker -9 when fill_missing = false): value map with the reference's 1e-6 tolerance in
+    f32 ("add" = identity), exact sum of the coded row, mean as f32(sum / n), centring in f32 -> (lut f32[m, 4] indexed
+    by the PLINK 2-bit code {hom-ref, missing, het, hom-alt}, coded_mean f32[m]).  The additive coding of filled rows does not
+    come through here (its sum involves the imputed value; jxb_decode_packed_prepared handles it)."""
     missing = np.asarray(missing, dtype=np.int64)
     het = np.asarray(het, dtype=np.int64)
     hom = np.asarray(hom_alt, dtype=np.int64)
@@ -207,8 +209,11 @@ def coded_row_lut(missing, het, hom_alt, imputed, n: int, coding: str):
     tol = np.float32(1e-6)
     near1 = np.abs(vals - np.float32(1.0)) <= tol
     near2 = np.abs(vals - np.float32(2.0)) <= tol
-    hit = {"dom": near1 | near2, "rec": near2, "het": near1}[coding]
-    coded = np.where(hit, np.float32(1.0), np.float32(0.0)).astype(np.float32)
+    if coding == "add":
+        coded = vals                                                      # integers (or the -9 marker): the sum stays exact
+    else:
+        hit = {"dom": near1 | near2, "rec": near2, "het": near1}[coding]
+        coded = np.where(hit, np.float32(1.0), np.float32(0.0)).astype(np.float32)
     cnt = np.stack([n - missing - het - hom, missing, het, hom], axis=1).astype(np.float64)
     total = (cnt * coded.astype(np.float64)).sum(axis=1)                 # 0/1 values times counts: an exact integer
     coded_mean = (total / float(n)).astype(np.float32)
@@ -223,8 +228,7 @@ class BedChunkReader:
         require_gpu()
         self.maf = 0.0 if maf_threshold is None else float(maf_threshold)
         self.miss = 1.0 if max_missing_rate is None else float(max_missing_rate)
-        if fill_missing is not None and not fill_missing:
-            raise NotImplementedError("fill_missing=False is not built (the LMM path always imputes)")
+        self._fill = True if fill_missing is None else bool(fill_missing)   # false: missing calls keep the decoder's -9
         model_key = (model or "add").lower()
         if model_key not in ("add", "dom", "rec", "het"):
             raise ValueError("model must be one of: add, dom, rec, het")
@@ -344,6 +348,8 @@ class BedChunkReader:
             packed = np.ascontiguousarray(self._packed[rows])
             counts, _, _, _ = self._dev.decode_packed(packed, self._n_full, sidx, 0.0, 1.0, 0.0, want_g=False)
             keep, flip, lut = raw_row_decisions(counts[:, 0], counts[:, 1], counts[:, 2], n, self.maf, self.miss, self.het)
+            if not self._fill:
+                lut[:, 1] = np.float32(-9.0)                              # gfcore.rs:468-476 skipped; 2 - g spares g < 0
             k = np.nonzero(keep)[0]
             if k.size == 0:
                 continue
@@ -380,14 +386,15 @@ class BedChunkReader:
             nk = int(keep.sum())
             if nk == 0:
                 continue
-            if coding_key != "add":
-                # dom / rec / het: the filled row takes four values {0, imputed, 1, 2}; the coding map, the exact f64 sum of
-                # the coded row and the f32 centring give four output values per row -> per-row LUT decode on the device
+            if coding_key != "add" or not self._fill:
+                # dom / rec / het, or unfilled rows: the row takes four values {0, imputed | -9, 1, 2}; the coding map, the exact
+                # f64 sum of the coded row and the f32 centring give four output values per row -> per-row LUT decode on the device
                 k = np.nonzero(keep)[0]
-                lut, coded_mean = coded_row_lut(counts[k, 0], counts[k, 1], counts[k, 2], imputed[k], n, coding_key)
+                fillv = imputed[k] if self._fill else np.full(k.shape[0], -9.0, dtype=np.float32)
+                lut, coded_mean = coded_row_lut(counts[k, 0], counts[k, 1], counts[k, 2], fillv, n, coding_key)
                 blocks.append(self._decode_lut(np.ascontiguousarray(packed[k]), lut))
                 sites.extend(self._sites[int(rows[i])] for i in k)
-                afs.append(coded_mean)
+                afs.append(coded_mean * np.float32(0.5) if coding_key == "add" else coded_mean)
                 misses.append(counts[k, 0].astype(np.float32))
                 m += nk
                 continue

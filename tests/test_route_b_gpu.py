@@ -318,3 +318,43 @@ def test_prepared_chunks_non_additive_codings(jx, oracle, tmp_path, coding):
             cm = np.float32(float(coded.astype(np.float64).sum()) / n)
             assert np.array_equal(g[out_r].view(np.uint32), (coded - cm).view(np.uint32)), (coding, i)
             assert af[out_r].view(np.uint32) == cm.view(np.uint32) and miss[out_r] == float((c == 1).sum())
+
+
+def test_reader_without_missing_fill(jx, oracle, tmp_path):
+    """fill_missing = false (src/io/gfcore.rs:468-476 skipped): next_chunk keeps -9 at missing calls (also in recoded rows),
+    next_chunk_prepared carries the marker through coding, mean and centring."""
+    from janusx_b200 import synth
+    from janusx_b200.gfreader import BedChunkReader
+    n, m = 61, 200
+    packed, _ = synth.draw_genotypes(m, n, seed=37, missing_rate=0.08)
+    packed[3] = 0b01010101                                   # a row with every call missing
+    prefix = str(tmp_path / "nofill")
+    synth.write_plink(prefix, packed, n)
+    codes = np.stack([(packed[:, j // 4] >> ((j % 4) * 2)) & 3 for j in range(n)], axis=1)
+    rd = BedChunkReader(prefix, maf_threshold=0.0, max_missing_rate=1.0, fill_missing=False)
+    gs, names = [], []
+    while True:
+        out = rd.next_chunk(64)
+        if out is None:
+            break
+        gs.append(out[0]); names.extend(s.snp for s in out[1])
+    g = np.concatenate(gs)
+    assert names == [f"snp{i}" for i in range(m)]
+    for i in range(m):
+        raw = np.array([0.0, -9.0, 1.0, 2.0], dtype=np.float32)[codes[i]]
+        nm = raw >= 0
+        if nm.any() and float(raw[nm].sum()) / (2.0 * nm.sum()) > 0.5:
+            raw[nm] = np.float32(2.0) - raw[nm]
+        assert np.array_equal(g[i].view(np.uint32), raw.view(np.uint32)), i
+    for coding in ("add", "rec"):
+        rd = BedChunkReader(prefix, maf_threshold=0.0, max_missing_rate=1.0, fill_missing=False)
+        gp, sites, af, miss, _ = _read_all(rd, 50, coding=coding)
+        assert gp.shape == (m, n)
+        for i in range(m):
+            raw = np.array([0.0, -9.0, 1.0, 2.0], dtype=np.float32)[codes[i]]
+            coded = raw if coding == "add" else np.where(np.abs(raw - np.float32(2.0)) <= np.float32(1e-6), np.float32(1.0),
+                                                         np.float32(0.0)).astype(np.float32)
+            cm = np.float32(float(coded.astype(np.float64).sum()) / n)
+            assert np.array_equal(gp[i].view(np.uint32), (coded - cm).view(np.uint32)), (coding, i)
+            assert af[i].view(np.uint32) == (cm * np.float32(0.5) if coding == "add" else cm).view(np.uint32)
+            assert miss[i] == float((codes[i] == 1).sum())

@@ -86,3 +86,28 @@ def test_coded_row_lut_equals_row_by_row_restatement(coding):
         want = coded - cm
         assert mean[r].view(np.uint32) == cm.view(np.uint32)
         assert np.array_equal(lut[r][codes[r]].view(np.uint32), want.view(np.uint32)), (coding, r)
+
+
+@pytest.mark.parametrize("coding", ["add", "dom", "het"])
+def test_coded_row_lut_unfilled_rows(coding):
+    """fill_missing = false: missing calls keep the decoder's -9 through the coding map, the mean and the centring."""
+    from janusx_b200.gfreader import coded_row_lut
+    rng = np.random.default_rng(6)
+    n = 29
+    codes = np.stack([rng.choice(4, size=n, p=[0.45, 0.15, 0.3, 0.1]) for _ in range(30)] + [np.ones(n, dtype=np.int64)])
+    missing, het, hom = (codes == 1).sum(1), (codes == 2).sum(1), (codes == 3).sum(1)
+    lut, mean = coded_row_lut(missing, het, hom, np.full(codes.shape[0], -9.0, dtype=np.float32), n, coding)
+    one, two, tol = np.float32(1.0), np.float32(2.0), np.float32(1e-6)
+    for r in range(codes.shape[0]):
+        raw = np.array([0.0, -9.0, 1.0, 2.0], dtype=np.float32)[codes[r]]
+        if coding == "add":
+            coded = raw.copy()
+        else:
+            h1, h2 = np.abs(raw - one) <= tol, np.abs(raw - two) <= tol
+            coded = np.where({"dom": h1 | h2, "het": h1}[coding], one, np.float32(0.0)).astype(np.float32)
+        total = 0.0
+        for v in coded:
+            total += float(v)
+        cm = np.float32(total / n)
+        assert mean[r].view(np.uint32) == cm.view(np.uint32)
+        assert np.array_equal(lut[r][codes[r]].view(np.uint32), (coded - cm).view(np.uint32)), (coding, r)
