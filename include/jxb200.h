@@ -291,6 +291,10 @@ size_t jxb_format_block(char* buf, size_t cap, size_t rows, const char* chrom, c
  * resident U^T in the Python front end). */
 void jxb_host_checksum(const void* data, size_t bytes, uint64_t out2[2]);
 
+/* The writer's number formatters (exact fast path for `{:.N}` / `{:.Ne}`) against their printf route on `count` values
+ * chosen to stress them (ties, near-ties, powers of ten, carries); returns the number of differing strings. */
+size_t jxb_selftest_format(size_t count, uint64_t seed, int prec, char* first_bad, size_t bad_cap);
+
 /* Header line for 3 / 4 / 6 result columns (AssocResultCols::header, src/io/assoc2tsv.rs:45-57); NULL otherwise. */
 const char* jxb_tsv_header(int out_cols);
 

@@ -110,6 +110,7 @@ SYMBOLS = {
     "jxb_format_block": (C.c_size_t, [_vp, C.c_size_t, C.c_size_t, C.c_char_p, _vp, C.c_char_p, C.c_char_p, C.c_char_p,
                                       _vp, _vp, _vp, C.c_int, C.c_int]),
     "jxb_tsv_header": (C.c_char_p, [C.c_int]),
+    "jxb_selftest_format": (C.c_size_t, [C.c_size_t, C.c_uint64, C.c_int, C.c_char_p, C.c_size_t]),
     "jxb_host_checksum": (None, [_vp, C.c_size_t, C.POINTER(C.c_uint64)]),
     "jxb_grm_create": (C.c_int, [C.c_int, C.c_size_t, _vp, C.c_size_t, C.c_int, C.POINTER(_vp)]),
     "jxb_grm_update": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, _vp, C.POINTER(QcCfg)]),

@@ -46,15 +46,23 @@ int fail(int code, const std::string& msg);
 
 namespace {
 
+// ---- number formatting ------------------------------------------------------------------------------------------------
+// The writer prints ten numbers per row; at more than a million rows per second and GPU the C library's exact-decimal
+// printf (~0.6 us per number) is the bottleneck of the file-level scan.  fmt_fixed / fmt_exp therefore scale the value by
+// an exactly representable power of ten, keep the rounding error of that one operation (fma), and round the exact
+// scaled value to an integer -- the correctly rounded decimal, i.e. the digits printf prints -- whenever the exact
+// value is clearly off a rounding boundary.  Ties, near-ties, exponents beyond 10^22 and non-finite values take the printf
+// route (`*_slow`), so the output is printf's in every case (tests compare 10^7 values per format).
+
 // Rust `{:.N}`: C "%.Nf" with Rust's spellings of the non-finite values
-size_t fmt_fixed(char* buf, size_t cap, double v, int prec) {
+size_t fmt_fixed_slow(char* buf, size_t cap, double v, int prec) {
     if (std::isnan(v)) return (size_t)snprintf(buf, cap, "NaN");
     if (std::isinf(v)) return (size_t)snprintf(buf, cap, v > 0 ? "inf" : "-inf");
     return (size_t)snprintf(buf, cap, "%.*f", prec, v);
 }
 
 // Rust `{:.Ne}`: mantissa as C "%.Ne", exponent without sign padding or leading zeros
-size_t fmt_exp(char* buf, size_t cap, double v, int prec) {
+size_t fmt_exp_slow(char* buf, size_t cap, double v, int prec) {
     if (std::isnan(v)) return (size_t)snprintf(buf, cap, "NaN");
     if (std::isinf(v)) return (size_t)snprintf(buf, cap, v > 0 ? "inf" : "-inf");
     char tmp[64];
@@ -64,6 +72,90 @@ size_t fmt_exp(char* buf, size_t cap, double v, int prec) {
     const int ex = atoi(tmp + epos + 1);
     tmp[epos] = '\0';
     return (size_t)snprintf(buf, cap, "%se%d", tmp, ex);
+}
+
+const double kPow10[23] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
+                           1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};   // exact doubles
+
+// nearest integer of the exact real a * 10^k (k in [-22, 22], result < 2^52); false when the exact value lies within
+// 2^-20 of a rounding boundary (ties included) -- the caller then lets printf decide
+inline bool scaled_round(double a, int k, uint64_t* q) {
+    if (k > 22 || k < -22) return false;
+    double t, frac_err;
+    if (k >= 0) {
+        t = a * kPow10[k];
+        frac_err = std::fma(a, kPow10[k], -t);                 // a * 10^k = t + frac_err exactly
+    } else {
+        t = a / kPow10[-k];
+        frac_err = std::fma(-t, kPow10[-k], a) / kPow10[-k];   // a / 10^-k = t + (a - t * 10^-k) / 10^-k; remainder exact
+    }
+    if (!(t < 4503599627370496.0)) return false;
+    const double fl = std::floor(t);
+    const double r = (t - fl) + frac_err;                      // fractional part of the exact value (|frac_err| <= ulp(t)/2)
+    if (std::fabs(r - 0.5) < 9.5367431640625e-07) return false;
+    *q = (uint64_t)fl + (r > 0.5 ? 1u : 0u);
+    return true;
+}
+
+inline char* put_uint(char* w, uint64_t v) {                   // decimal digits of v, no padding
+    char tmp[24];
+    int n = 0;
+    do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+    while (n) *w++ = tmp[--n];
+    return w;
+}
+
+size_t fmt_fixed(char* buf, size_t cap, double v, int prec) {
+    const double a = std::fabs(v);
+    uint64_t q;
+    if (!(a < 1e11) || prec < 1 || prec > 9 || cap < 40 || !scaled_round(a, prec, &q)) return fmt_fixed_slow(buf, cap, v, prec);
+    char* w = buf;
+    if (std::signbit(v)) *w++ = '-';
+    const uint64_t scale = (uint64_t)kPow10[prec];
+    w = put_uint(w, q / scale);
+    *w++ = '.';
+    uint64_t f = q % scale;
+    for (int i = prec - 1; i >= 0; --i) { w[i] = (char)('0' + f % 10); f /= 10; }
+    w += prec;
+    *w = '\0';
+    return (size_t)(w - buf);
+}
+
+size_t fmt_exp(char* buf, size_t cap, double v, int prec) {
+    const double a = std::fabs(v);
+    if (!(a >= 1e-17 && a < 1e21) || prec < 1 || prec > 9 || cap < 40) return fmt_exp_slow(buf, cap, v, prec);
+    // decimal exponent E with 10^E <= a < 10^(E+1): estimate from the binary exponent, then settle it exactly
+    int e2;
+    (void)std::frexp(a, &e2);
+    int E = (int)std::floor((e2 - 1) * 0.30102999566398120);
+    auto at_least_pow10 = [&](int e) {                          // a >= 10^e, exactly
+        if (e >= 0) return a >= kPow10[e];
+        const double t = a * kPow10[-e];
+        const double err = std::fma(a, kPow10[-e], -t);
+        return t > 1.0 || (t == 1.0 && err >= 0.0);
+    };
+    if (E < -22 || E > 21) return fmt_exp_slow(buf, cap, v, prec);
+    if (!at_least_pow10(E)) --E;
+    else if (E + 1 <= 22 && E + 1 >= -22 && at_least_pow10(E + 1)) ++E;
+    if (E < -22 || E > 21) return fmt_exp_slow(buf, cap, v, prec);
+    uint64_t q;
+    if (!scaled_round(a, prec - E, &q)) return fmt_exp_slow(buf, cap, v, prec);
+    const uint64_t top = (uint64_t)kPow10[prec + 1];
+    if (q >= top) { q /= 10; ++E; }                             // 9.99996 -> 1.0000e(E+1): q == 10^(prec+1) exactly
+    if (q < top / 10) return fmt_exp_slow(buf, cap, v, prec);    // cannot happen; printf as the safety net
+    char* w = buf;
+    if (std::signbit(v)) *w++ = '-';
+    const uint64_t scale = (uint64_t)kPow10[prec];
+    *w++ = (char)('0' + q / scale);
+    *w++ = '.';
+    uint64_t f = q % scale;
+    for (int i = prec - 1; i >= 0; --i) { w[i] = (char)('0' + f % 10); f /= 10; }
+    w += prec;
+    *w++ = 'e';
+    if (E < 0) { *w++ = '-'; w = put_uint(w, (uint64_t)(-E)); }
+    else w = put_uint(w, (uint64_t)E);
+    *w = '\0';
+    return (size_t)(w - buf);
 }
 
 // Pinned staging buffers are kept between calls (page-locking hundreds of MB costs more than a small scan):
@@ -352,10 +444,16 @@ static size_t format_row_impl(char* buf, size_t cap, Str chrom, int64_t pos, Str
     auto put_s = [&](Str t) { const size_t room = (size_t)(end - w) - 1; const size_t c = t.n < room ? t.n : room; memcpy(w, t.p, c); w += c; };
     auto tab = [&]() { if (w < end - 1) *w++ = '\t'; };
     put_s(chrom); tab();
-    adv((size_t)snprintf(w, (size_t)(end - w), "%lld", (long long)pos)); tab();
+    // (cap >= format_row_need(): 21 bytes of a decimal int64 always fit)
+    auto put_pos = [&]() {
+        if (pos < 0) { *w++ = '-'; w = put_uint(w, (uint64_t)0 - (uint64_t)pos); }
+        else w = put_uint(w, (uint64_t)pos);
+    };
+    put_pos(); tab();
     if (resolve_name && (snp.n == 0 || (snp.n == 1 && snp.p[0] == '.'))) {
         put_s(chrom);
-        adv((size_t)snprintf(w, (size_t)(end - w), "_%lld", (long long)pos));
+        if (w < end - 1) *w++ = '_';
+        put_pos();
     } else {
         put_s(snp);
     }
@@ -448,6 +546,63 @@ extern "C" void jxb_host_checksum(const void* data, size_t bytes, uint64_t out2[
     const uint8_t* tail = (const uint8_t*)data + words * 8;
     for (size_t i = 0; i < bytes % 8; ++i) a = a * 1099511628211ull + tail[i];
     out2[0] = a; out2[1] = x;
+}
+
+// fmt_fixed / fmt_exp against their printf routes on `count` doubles drawn to stress them: uniform bit patterns over the
+// exponent range the columns see, short decimals (exact ties and near-ties at the printed precision), neighbours of powers
+// of ten, f32 values, integers.  Returns the number of differing strings; the first one is described in `first_bad`.
+extern "C" size_t jxb_selftest_format(size_t count, uint64_t seed, int prec, char* first_bad, size_t bad_cap) {
+    uint64_t st = seed * 0x9E3779B97F4A7C15ull + 0x1234567ull;
+    auto next = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return st; };
+    size_t bad = 0;
+    char a[96], b[96];
+    if (first_bad && bad_cap) first_bad[0] = '\0';
+    for (size_t i = 0; i < count; ++i) {
+        const uint64_t r = next();
+        double v;
+        switch (i % 8) {
+            case 0: case 1: {   // random mantissa, binary exponent in [-80, 80]
+                const int ex = (int)(next() % 161) - 80;
+                v = std::ldexp(1.0 + (double)(r >> 12) / 4503599627370496.0, ex);
+                break;
+            }
+            case 2: {           // short decimals: j / 10^d with d up to prec + 2 (ties at the printed precision are j = ...5)
+                const int d = (int)(next() % (unsigned)(prec + 3));
+                v = (double)(r % 20000000ull) / kPow10[d];
+                break;
+            }
+            case 3: {           // dyadic fractions k / 2^s: exactly representable ties (0.03125 = 312.5e-4)
+                v = (double)(r % 100000ull) / (double)(1ull << (next() % 12));
+                break;
+            }
+            case 4: {           // neighbours of powers of ten
+                const int e = (int)(next() % 41) - 20;
+                const double p10 = e >= 0 ? kPow10[e] : 1.0 / kPow10[-e];
+                v = p10;
+                const int steps = (int)(r % 7) - 3;
+                for (int q = 0; q < (steps < 0 ? -steps : steps); ++q) v = std::nextafter(v, steps < 0 ? 0.0 : 1e300);
+                break;
+            }
+            case 5: v = (double)(float)std::ldexp(1.0 + (double)(r >> 41) / 8388608.0, (int)(next() % 40) - 30); break;   // f32
+            case 6: v = (double)(r % 1000000000ull); break;
+            default: {          // 9.9999x-type mantissas at every decade: carries into the next exponent
+                const int e = (int)(next() % 31) - 15;
+                const double m = 9.9 + (double)(r % 100000ull) / 1000000.0;
+                v = e >= 0 ? m * kPow10[e] : m / kPow10[-e];
+                break;
+            }
+        }
+        if (next() & 1) v = -v;
+        for (int kind = 0; kind < 2; ++kind) {
+            if (kind == 0) { fmt_fixed(a, sizeof a, v, prec); fmt_fixed_slow(b, sizeof b, v, prec); }
+            else { fmt_exp(a, sizeof a, v, prec); fmt_exp_slow(b, sizeof b, v, prec); }
+            if (strcmp(a, b) != 0) {
+                if (bad == 0 && first_bad && bad_cap) snprintf(first_bad, bad_cap, "%s of %.17g: fast '%s' printf '%s'", kind ? "exp" : "fixed", v, a, b);
+                ++bad;
+            }
+        }
+    }
+    return bad;
 }
 
 extern "C" const char* jxb_tsv_header(int out_cols) {

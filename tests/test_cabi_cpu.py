@@ -270,3 +270,25 @@ def test_prepared_meta_row_decisions_host_logic():
             else:
                 keep = min(af_i, np.float32(1) - af_i) >= np.float32(maf_t)
             assert keep == k[i] and mr_i == mr[i] and af_i == af[i], (i, maf_t)
+
+
+def test_number_formatters_equal_printf():
+    """The TSV writer's exact fast path for `{:.4}` / `{:.4e}` / `{:.6e}` (src/io/assoc2tsv.rs:430-517 prints with Rust's
+    correctly rounded formatter) must print what the printf route prints: ties and near-ties at the printed precision,
+    neighbours of powers of ten, carries into the next decade, f32 values, either sign."""
+    import ctypes as C
+    from janusx_b200 import _cabi
+    lib = _cabi.lib()
+    for prec in (4, 6):
+        msg = C.create_string_buffer(256)
+        bad = lib.jxb_selftest_format(1_500_000, 20260609 + prec, prec, msg, 256)
+        assert bad == 0, msg.value.decode()
+    # spot values through the row formatter: a tie (0.03125 -> 312.5e-4), a negative that rounds to zero, a carry, a tiny p
+    buf = C.create_string_buffer(4096)
+    row = (C.c_double * 3)(-0.00004, 9.99996, 3.2e-301)
+    n = lib.jxb_format_row(buf, 4096, b"7", -12, b".", b"A", b"G", C.c_float(0.03125), C.c_float(0.5), row, 3)
+    want = "7\t-12\t7_-12\tA\tG\t%.4f\t%.4f\t%.4f\t%.4f\t" % (0.03125, 0.5, -0.00004, 9.99996)
+    z = (-0.00004 / 9.99996) ** 2
+    m, e = ("%.4e" % z).split("e")
+    want += f"{m}e{int(e)}\t3.2000e-301\n"
+    assert buf.raw[:n].decode() == want
